@@ -1,0 +1,407 @@
+// HBM-bound byte/elementwise kernels of the decode path: entropy-index computation, dequantisation,
+// FSQ code expansion, depthwise 3x3, nearest upsample, attention window (un)partition, x0 combine.
+#include "../../include/onedc_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace onedc {
+
+// step k, pixel parity p = 2*(y&1) + (x&1): active 32-channel group = p ^ kXor[k]
+// (get_mask_four_parts, reference compression_model.py:269-283)
+__device__ __constant__ int kXor[4] = {0, 3, 2, 1};
+
+// ------------------------------------------------------------------------------------------------
+// scales (NHWC bf16, 4*c4 channels) -> int16 CDF indices in stream order [n][c4][h*w].
+// Block = 128 consecutive pixels of one image: gather the active c4-channel slice (contiguous 2*c4 bytes
+// per pixel), LUT each value, transpose through shared memory, write 256 contiguous bytes per plane.
+template <int C4>
+__global__ void __launch_bounds__(128) scale_to_index_kernel(const __nv_bfloat16* scales, long long ld, const uint8_t* lut,
+                                                             int16_t* idx_out, int step, int h, int w) {
+  __shared__ int16_t tile[C4][128 + 2];
+  const long long hw = (long long)h * w;
+  const int n = blockIdx.y;
+  const long long p = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (p < hw) {
+    const int y = (int)(p / w), x = (int)(p - (long long)y * w);
+    const int g = (2 * (y & 1) + (x & 1)) ^ kXor[step];
+    const uint4* src = reinterpret_cast<const uint4*>(scales + ((long long)n * hw + p) * ld + g * C4);
+#pragma unroll
+    for (int v = 0; v < C4 / 8; v++) {
+      uint4 q = __ldg(src + v);
+      uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        tile[v * 8 + 2 * j][threadIdx.x] = (int16_t)__ldg(lut + (wds[j] & 0xFFFFu));
+        tile[v * 8 + 2 * j + 1][threadIdx.x] = (int16_t)__ldg(lut + (wds[j] >> 16));
+      }
+    }
+  }
+  __syncthreads();
+  if (p < hw) {
+    int16_t* dst = idx_out + (long long)n * C4 * hw + p;
+#pragma unroll 8
+    for (int c = 0; c < C4; c++) dst[(long long)c * hw] = tile[c][threadIdx.x];
+  }
+}
+
+// generic elementwise build_indexes (int32 out)
+__global__ void build_indexes_kernel(const void* scales, int dtype, const uint8_t* lut, const float* thr, int32_t* out,
+                                     long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (dtype == DT_BF16) {
+      out[i] = __ldg(lut + reinterpret_cast<const uint16_t*>(scales)[i]);
+    } else {
+      const float s = reinterpret_cast<const float*>(scales)[i];
+      int lo = 0, hi = 255;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s >= __ldg(thr + mid)) lo = mid + 1; else hi = mid;
+      }
+      out[i] = lo;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// y_hat[n,y,x,g*C4+c] = bf16( sym[n][c][y*w+x] + means[n,y,x,g*C4+c] )   (sym may be null: means only)
+// MODE 0: decode (sym given or null).  MODE 1: encode twin, sym is OUTPUT = clamp(rint(y - means)).
+template <int C4, int MODE>
+__global__ void __launch_bounds__(128) dequant_kernel(int16_t* sym, const __nv_bfloat16* yin, long long yin_ld,
+                                                      const __nv_bfloat16* means, long long means_ld, __nv_bfloat16* y_hat,
+                                                      long long y_ld, int step, int h, int w) {
+  __shared__ int16_t tile[C4][128 + 2];
+  const long long hw = (long long)h * w;
+  const int n = blockIdx.y;
+  const long long p = (long long)blockIdx.x * 128 + threadIdx.x;
+  const bool ok = p < hw;
+  if (MODE == 0 && sym != nullptr && ok) {
+    const int16_t* src = sym + (long long)n * C4 * hw + p;
+#pragma unroll 8
+    for (int c = 0; c < C4; c++) tile[c][threadIdx.x] = src[(long long)c * hw];
+  }
+  // (each thread only touches its own column of the tile, no barrier needed in MODE 0)
+  if (ok) {
+    const int y = (int)(p / w), x = (int)(p - (long long)y * w);
+    const int g = (2 * (y & 1) + (x & 1)) ^ kXor[step];
+    const long long pix = (long long)n * hw + p;
+    const uint4* mp = reinterpret_cast<const uint4*>(means + pix * means_ld + g * C4);
+    uint4* dst = reinterpret_cast<uint4*>(y_hat + pix * y_ld + g * C4);
+    const uint4* yp = MODE == 1 ? reinterpret_cast<const uint4*>(yin + pix * yin_ld + g * C4) : nullptr;
+#pragma unroll
+    for (int v = 0; v < C4 / 8; v++) {
+      uint4 m = __ldg(mp + v);
+      uint32_t mw[4] = {m.x, m.y, m.z, m.w}, ow[4];
+      uint32_t yw[4] = {0, 0, 0, 0};
+      if (MODE == 1) {
+        uint4 yy = __ldg(yp + v);
+        yw[0] = yy.x; yw[1] = yy.y; yw[2] = yy.z; yw[3] = yy.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        float q0, q1;
+        if (MODE == 1) {
+          q0 = fminf(fmaxf(rintf(bf16lo(yw[j]) - bf16lo(mw[j])), -30000.f), 30000.f);
+          q1 = fminf(fmaxf(rintf(bf16hi(yw[j]) - bf16hi(mw[j])), -30000.f), 30000.f);
+          tile[v * 8 + 2 * j][threadIdx.x] = (int16_t)q0;
+          tile[v * 8 + 2 * j + 1][threadIdx.x] = (int16_t)q1;
+        } else if (sym != nullptr) {
+          q0 = (float)tile[v * 8 + 2 * j][threadIdx.x];
+          q1 = (float)tile[v * 8 + 2 * j + 1][threadIdx.x];
+        } else {
+          q0 = q1 = 0.f;
+        }
+        // the reference casts the decoded symbols to the activation dtype (bf16) before adding the means
+        // (entropy_models.py:374 `.to(dtype)`): |q| > 256 is rounded to bf16 first
+        q0 = __bfloat162float(__float2bfloat16(q0));
+        q1 = __bfloat162float(__float2bfloat16(q1));
+        ow[j] = pack_bf16x2(q0 + bf16lo(mw[j]), q1 + bf16hi(mw[j]));
+      }
+      dst[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+    if (step == 0) {   // y_hat_so_far starts as (..)*mask_0: zero everywhere else
+      for (int og = 0; og < 4; og++) {
+        if (og == g) continue;
+        uint4* z = reinterpret_cast<uint4*>(y_hat + pix * y_ld + og * C4);
+#pragma unroll
+        for (int v = 0; v < C4 / 8; v++) z[v] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    if (MODE == 1) {
+      int16_t* o = sym + (long long)n * C4 * hw + p;
+#pragma unroll 8
+      for (int c = 0; c < C4; c++) o[(long long)c * hw] = tile[c][threadIdx.x];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void fsq_codes_kernel(const int32_t* idx, __nv_bfloat16* out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int v = idx[i];
+    float c[8];
+#pragma unroll
+    for (int d = 0; d < 7; d++) c[d] = (float)(((v >> (2 * d)) & 3) - 2) * 0.5f;
+    c[7] = 0.f;
+    uint4 q;
+    q.x = pack_bf16x2(c[0], c[1]); q.y = pack_bf16x2(c[2], c[3]);
+    q.z = pack_bf16x2(c[4], c[5]); q.w = pack_bf16x2(c[6], c[7]);
+    reinterpret_cast<uint4*>(out)[i] = q;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise 3x3, pad 1, NHWC bf16; weights fp32 [9][C], bias fp32 [C]
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const __nv_bfloat16* x, const float* w9c, const float* bias,
+                                                        __nv_bfloat16* out, int n_img, int h, int w, int c) {
+  const int nvec = c >> 3;
+  const long long total = (long long)n_img * h * w * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    long long pix = i / nvec;
+    const int xx = (int)(pix % w);
+    const long long t = pix / w;
+    const int yy = (int)(t % h);
+    const int n = (int)(t / h);
+    float acc[8];
+    {
+      const float4* b4 = reinterpret_cast<const float4*>(bias + v * 8);
+      float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+      const int iy = yy + ky - 1;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; kx++) {
+        const int ix = xx + kx - 1;
+        if (ix < 0 || ix >= w) continue;
+        uint4 q = __ldg(reinterpret_cast<const uint4*>(x + (((long long)n * h + iy) * w + ix) * c + v * 8));
+        const float4* w4 = reinterpret_cast<const float4*>(w9c + (ky * 3 + kx) * c + v * 8);
+        float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);
+        acc[0] += bf16lo(q.x) * w0.x; acc[1] += bf16hi(q.x) * w0.y; acc[2] += bf16lo(q.y) * w0.z; acc[3] += bf16hi(q.y) * w0.w;
+        acc[4] += bf16lo(q.z) * w1.x; acc[5] += bf16hi(q.z) * w1.y; acc[6] += bf16lo(q.w) * w1.z; acc[7] += bf16hi(q.w) * w1.w;
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+    reinterpret_cast<uint4*>(out)[i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* x, uint4* out, int n_img, int h, int w, int nvec) {
+  const long long total = (long long)n_img * (2 * h) * (2 * w) * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    long long pix = i / nvec;
+    const int xo = (int)(pix % (2 * w));
+    const long long t = pix / (2 * w);
+    const int yo = (int)(t % (2 * h));
+    const int n = (int)(t / (2 * h));
+    out[i] = __ldg(x + (((long long)n * h + (yo >> 1)) * w + (xo >> 1)) * nvec + v);
+  }
+}
+
+// windows of win x win pixels -> [n*nwy*nwx][win*win tokens][c]; tokens of an edge window are
+// enumerated row-major over its valid vh x vw extent, the rest of the window's rows are zero.
+__global__ void __launch_bounds__(256) window_partition_kernel(const uint4* x, uint4* out, int n_img, int h, int w, int nvec,
+                                                               int win) {
+  const int nwy = (h + win - 1) / win, nwx = (w + win - 1) / win;
+  const long long total = (long long)n_img * nwy * nwx * win * win * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    long long t = i / nvec;
+    const int tok = (int)(t % (win * win));
+    t /= (win * win);
+    const int wx = (int)(t % nwx);
+    t /= nwx;
+    const int wy = (int)(t % nwy);
+    const int n = (int)(t / nwy);
+    const int vw = min(win, w - wx * win), vh = min(win, h - wy * win);
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (tok < vw * vh) {
+      const int ly = tok / vw, lx = tok - ly * vw;
+      val = __ldg(x + (((long long)n * h + wy * win + ly) * w + wx * win + lx) * nvec + v);
+    }
+    out[i] = val;
+  }
+}
+
+__global__ void __launch_bounds__(256) window_merge_kernel(const uint4* a, const uint4* res, uint4* out, int n_img, int h, int w,
+                                                           int nvec, int win) {
+  const int nwy = (h + win - 1) / win, nwx = (w + win - 1) / win;
+  const long long total = (long long)n_img * h * w * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    long long pix = i / nvec;
+    const int xx = (int)(pix % w);
+    const long long t = pix / w;
+    const int yy = (int)(t % h);
+    const int n = (int)(t / h);
+    const int wy = yy / win, wx = xx / win;
+    const int vw = min(win, w - wx * win);
+    const int tok = (yy - wy * win) * vw + (xx - wx * win);
+    uint4 q = __ldg(a + ((((long long)n * nwy + wy) * nwx + wx) * win * win + tok) * nvec + v);
+    if (res != nullptr) {
+      uint4 r = __ldg(res + i);
+      q.x = pack_bf16x2(bf16lo(q.x) + bf16lo(r.x), bf16hi(q.x) + bf16hi(r.x));
+      q.y = pack_bf16x2(bf16lo(q.y) + bf16lo(r.y), bf16hi(q.y) + bf16hi(r.y));
+      q.z = pack_bf16x2(bf16lo(q.z) + bf16lo(r.z), bf16hi(q.z) + bf16hi(r.z));
+      q.w = pack_bf16x2(bf16lo(q.w) + bf16lo(r.w), bf16hi(q.w) + bf16hi(r.w));
+    }
+    out[i] = q;
+  }
+}
+
+struct PqW {
+  float w[16];
+  float b[4];
+};
+__global__ void x0_prepare_kernel(const float4* reduced, const float4* eps, float sa, float s1m, float inv_scaling, PqW pq,
+                                  uint4* out_hilo, float4* x0_out, long long pixels) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels; i += (long long)gridDim.x * blockDim.x) {
+    const float4 r = reduced[i], e = eps[i];
+    float x0[4] = {(r.x - s1m * e.x) / sa, (r.y - s1m * e.y) / sa, (r.z - s1m * e.z) / sa, (r.w - s1m * e.w) / sa};
+    if (x0_out != nullptr) x0_out[i] = make_float4(x0[0], x0[1], x0[2], x0[3]);
+    float z[4], hi[4], lo[4];
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+      float acc = pq.b[o];
+#pragma unroll
+      for (int c = 0; c < 4; c++) acc += pq.w[o * 4 + c] * (x0[c] * inv_scaling);
+      z[o] = acc;
+      hi[o] = __bfloat162float(__float2bfloat16(acc));
+      lo[o] = z[o] - hi[o];
+    }
+    uint4 q;
+    q.x = pack_bf16x2(hi[0], hi[1]); q.y = pack_bf16x2(hi[2], hi[3]);
+    q.z = pack_bf16x2(lo[0], lo[1]); q.w = pack_bf16x2(lo[2], lo[3]);
+    out_hilo[i] = q;
+  }
+}
+
+static inline int ew_blocks(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace onedc
+
+using namespace onedc;
+
+extern "C" int onedc_scale_to_index(const void* scales, int64_t ld, const uint8_t* lut, int16_t* idx_out, int32_t step,
+                                    int32_t n_img, int32_t h, int32_t w, int32_t c4, void* stream) {
+  ONEDC_CHECK(c4 == 32 && step >= 0 && step < 4 && ld % 8 == 0, "scale_to_index: c4 must be 32, step in 0..3");
+  ONEDC_CHECK(n_img <= 65535, "scale_to_index: batch too large");
+  const long long hw = (long long)h * w;
+  dim3 grid((unsigned)((hw + 127) / 128), n_img);
+  scale_to_index_kernel<32><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)scales, ld, lut, idx_out, step, h, w);
+  count_launch();
+  ONEDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int onedc_build_indexes(const void* scales, int32_t in_dtype, const uint8_t* lut, const float* thresholds,
+                                   int32_t* idx_out, int64_t n, void* stream) {
+  ONEDC_CHECK((in_dtype == DT_BF16 && lut) || (in_dtype == DT_F32 && thresholds), "build_indexes: missing table");
+  build_indexes_kernel<<<ew_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(scales, in_dtype, lut, thresholds, idx_out, n);
+  count_launch();
+  ONEDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int onedc_dequant_accum(const int16_t* sym, const void* means, int64_t means_ld, void* y_hat, int64_t y_ld,
+                                   int32_t step, int32_t n_img, int32_t h, int32_t w, int32_t c4, void* stream) {
+  ONEDC_CHECK(c4 == 32 && step >= 0 && step < 4 && means_ld % 8 == 0 && y_ld % 8 == 0, "dequant_accum: bad arguments");
+  const long long hw = (long long)h * w;
+  dim3 grid((unsigned)((hw + 127) / 128), n_img);
+  dequant_kernel<32, 0><<<grid, 128, 0, (cudaStream_t)stream>>>(const_cast<int16_t*>(sym), nullptr, 0,
+                                                               (const __nv_bfloat16*)means, means_ld,
+                                                               (__nv_bfloat16*)y_hat, y_ld, step, h, w);
+  count_launch();
+  ONEDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int onedc_quantize_residual(const void* y, int64_t y_in_ld, const void* means, int64_t means_ld, int16_t* sym,
+                                       void* y_hat, int64_t y_ld, int32_t step, int32_t n_img, int32_t h, int32_t w,
+                                       int32_t c4, void* stream) {
+  ONEDC_CHECK(c4 == 32 && step >= 0 && step < 4 && means_ld % 8 == 0 && y_ld % 8 == 0 && y_in_ld % 8 == 0,
+              "quantize_residual: bad arguments");
+  const long long hw = (long long)h * w;
+  dim3 grid((unsigned)((hw + 127) / 128), n_img);
+  dequant_kernel<32, 1><<<grid, 128, 0, (cudaStream_t)stream>>>(sym, (const __nv_bfloat16*)y, y_in_ld,
+                                                               (const __nv_bfloat16*)means, means_ld,
+                                                               (__nv_bfloat16*)y_hat, y_ld, step, h, w);
+  count_launch();
+  ONEDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int onedc_fsq_codes(const int32_t* idx, void* out, int64_t n, void* stream) {
+  fsq_codes_kernel<<<ew_blocks(n, 128), 128, 0, (cudaStream_t)stream>>>(idx, (__nv_bfloat16*)out, n);
+  count_launch();
+  ONEDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int onedc_dwconv3x3(const void* x, const float* w9c, const float* bias, void* out, int32_t n_img, int32_t h,
+                               int32_t w, int32_t c, void* stream) {
+  ONEDC_CHECK(c % 8 == 0, "dwconv3x3: C must be a multiple of 8");
+  const long long total = (long long)n_img * h * w * (c / 8);
+  dwconv3x3_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, w9c, bias,
+                                                                           (__nv_bfloat16*)out, n_img, h, w, c);
+  count_launch();
+  ONEDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int onedc_upsample2x(const void* x, void* out, int32_t n_img, int32_t h, int32_t w, int32_t c, void* stream) {
+  ONEDC_CHECK(c % 8 == 0, "upsample2x: C must be a multiple of 8");
+  const long long total = (long long)n_img * 4 * h * w * (c / 8);
+  upsample2x_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, n_img, h, w, c / 8);
+  count_launch();
+  ONEDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int onedc_window_partition(const void* x, void* out, int32_t n_img, int32_t h, int32_t w, int32_t c, int32_t win,
+                                      void* stream) {
+  ONEDC_CHECK(c % 8 == 0, "window_partition: C must be a multiple of 8");
+  const int nwy = (h + win - 1) / win, nwx = (w + win - 1) / win;
+  const long long total = (long long)n_img * nwy * nwx * win * win * (c / 8);
+  window_partition_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, n_img, h, w,
+                                                                                  c / 8, win);
+  count_launch();
+  ONEDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int onedc_window_merge(const void* attn_out, const void* residual, void* out, int32_t n_img, int32_t h, int32_t w,
+                                  int32_t c, int32_t win, void* stream) {
+  ONEDC_CHECK(c % 8 == 0, "window_merge: C must be a multiple of 8");
+  const long long total = (long long)n_img * h * w * (c / 8);
+  window_merge_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)attn_out, (const uint4*)residual,
+                                                                              (uint4*)out, n_img, h, w, c / 8, win);
+  count_launch();
+  ONEDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int onedc_x0_prepare(const float* reduced, const float* eps, float sqrt_alpha, float sqrt_one_minus_alpha,
+                                float inv_scaling, const float* pq_w, const float* pq_b, void* out_hilo, float* x0_out,
+                                int64_t pixels, void* stream) {
+  PqW pq;
+  for (int i = 0; i < 16; i++) pq.w[i] = pq_w[i];   // host pointers: 4x4 weight + bias of post_quant_conv
+  for (int i = 0; i < 4; i++) pq.b[i] = pq_b[i];
+  x0_prepare_kernel<<<ew_blocks(pixels, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)reduced, (const float4*)eps,
+                                                                             sqrt_alpha, sqrt_one_minus_alpha, inv_scaling,
+                                                                             pq, (uint4*)out_hilo, (float4*)x0_out, pixels);
+  count_launch();
+  ONEDC_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,657 @@
+// Implicit-GEMM convolution / GEMM for sm_100a.
+//
+//   out[pixel, n] = epilogue( sum_{tap, c} A[pixel shifted by tap, c] * W[tap][n][c] )
+//
+// * A is NHWC bf16.  One CTA tile = 128 output pixels arranged as a TH x TW spatial box, so that for
+//   every filter tap the A operand of the tile is ONE TMA box {64 ch, TW, 1, TH, 1} of a 5-D tensor map
+//   shifted by the tap offset; TMA's out-of-bounds zero fill IS the convolution's zero padding (and the
+//   K / M / N tails).  No im2col buffer exists anywhere.  Stride-2 convs use the parity view
+//   (c' = px*S + c, x/2, py, y/2, n) of the same tensor, a plain GEMM is the degenerate H = 1, 1-tap case,
+//   a batched GEMM takes one weight matrix per image, and a channel concat is a second tensor map
+//   visited by the same K loop.
+// * MMA: tcgen05.mma cta_group::1 kind::f16, M = 128, N = BN (16..256), K = 16 per instruction, operands in
+//   128B-swizzled shared memory written by TMA, fp32 accumulators in TMEM (two buffers of 256 columns so the
+//   epilogue of tile i overlaps the main loop of tile i+1).
+// * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..5 =
+//   epilogue (tcgen05.ld -> bias/activation/pair-ops/residual -> global).  Persistent CTAs, static
+//   round-robin tile schedule.
+//
+// The SIMT kernel at the bottom evaluates the same descriptor with scalar loops; it exists to check the
+// tensor-core kernel on the GPU (tests, impl = 1) and is never used by the decode path.
+#include <stdarg.h>
+
+#include <mutex>
+
+#include "../../include/onedc_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace onedc {
+
+constexpr int kMaxStages = 8;
+constexpr int kABytes = 128 * 128;       // 128 rows x 64 bf16
+constexpr int kSmemBudget = 200 * 1024;  // operand ring
+constexpr int kThreads = 192;
+
+struct IgemmParams {
+  // geometry
+  int n_img, H, W;        // output dims
+  int TH, TW, tiles_y, tiles_x;
+  int cout, BN, n_tiles, m_tiles;
+  int taps, kchunks[2], c1_off;
+  int tap_dc[9], tap_dx[9], tap_dp[9], tap_dy[9];
+  int w_batched;
+  int stages, stage_bytes;
+  // epilogue
+  const float* bias;
+  int epi_mode, act;
+  float slope;
+  const void* res;
+  int res_dtype;
+  long long res_ld;
+  void* out;
+  int out_dtype;
+  long long out_ld;
+  int out_col_off, store_mode, ps_c;
+  int ncols_out;          // cout (plain) or cout/2 (pair modes)
+  int vec_ok;
+  // raw views for the SIMT checker
+  const __nv_bfloat16* a_ptr[2];
+  int a_c[2];
+  long long a_pix[2];
+  int h_in, w_in, ksize, stride;
+  const __nv_bfloat16* w_ptr;
+  int ktot;
+  long long w_row, w_z;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue for 16 consecutive output columns of one pixel (shared by both kernels).
+//   a[16]: accumulator columns gcol .. gcol+15 (GEMM column space); b[16]: partner columns (pair modes)
+//   gcol_a / gcol_b: GEMM columns of a[0] / b[0] (bias index); ocol: first output column
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue16(const IgemmParams& p, int img, int y, int x, int gcol_a, int gcol_b,
+                                           int ocol, const float* a, const float* b) {
+  int ncols = p.ncols_out - ocol;
+  if (ncols <= 0) return;
+  if (ncols > 16) ncols = 16;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    float va = a[j];
+    if (p.bias != nullptr && j < ncols) va += __ldg(p.bias + gcol_a + j);
+    if (p.epi_mode == EPI_PLAIN) {
+      v[j] = act_apply(va, p.act, p.slope);
+    } else {
+      float vb = b[j];
+      if (p.bias != nullptr && j < ncols) vb += __ldg(p.bias + gcol_b + j);
+      if (p.epi_mode == EPI_PAIR_LRELU)
+        v[j] = (va > 0.f ? va : 0.1f * va) + (vb > 0.f ? vb : 0.01f * vb);
+      else
+        v[j] = va * (0.5f * vb * (1.f + erff(vb * 0.70710678118654752f)));
+    }
+  }
+  const long long pix = ((long long)img * p.H + y) * p.W + x;
+  if (p.res != nullptr) {
+    if (p.res_dtype == DT_BF16) {
+      const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.res_ld + ocol;
+      if (ncols == 16 && p.vec_ok) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(r);
+        uint4 q0 = __ldg(r4), q1 = __ldg(r4 + 1);
+        uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          v[2 * j] += bf16lo(w[j]);
+          v[2 * j + 1] += bf16hi(w[j]);
+        }
+      } else {
+        for (int j = 0; j < ncols; j++) v[j] += __bfloat162float(r[j]);
+      }
+    } else {
+      const float* r = reinterpret_cast<const float*>(p.res) + pix * p.res_ld + ocol;
+      for (int j = 0; j < ncols; j++) v[j] += __ldg(r + j);
+    }
+  }
+  if (p.store_mode == ST_TRANSPOSED) {
+    const long long pin = (long long)y * p.W + x;
+    for (int j = 0; j < ncols; j++) {
+      long long o = ((long long)img * p.ncols_out + ocol + j) * p.out_ld + pin;
+      if (p.out_dtype == DT_BF16)
+        reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(v[j]);
+      else
+        reinterpret_cast<float*>(p.out)[o] = v[j];
+    }
+    return;
+  }
+  long long opix = pix;
+  int oc = ocol;
+  if (p.store_mode == ST_PIXSHUF) {
+    int q = ocol / p.ps_c;
+    oc = ocol - q * p.ps_c;
+    opix = ((long long)img * (2 * p.H) + (2 * y + (q >> 1))) * (2 * p.W) + (2 * x + (q & 1));
+  }
+  const long long o = opix * p.out_ld + p.out_col_off + oc;
+  if (p.out_dtype == DT_BF16) {
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + o;
+    if (ncols == 16 && p.vec_ok) {
+      uint4 q0, q1;
+      q0.x = pack_bf16x2(v[0], v[1]);
+      q0.y = pack_bf16x2(v[2], v[3]);
+      q0.z = pack_bf16x2(v[4], v[5]);
+      q0.w = pack_bf16x2(v[6], v[7]);
+      q1.x = pack_bf16x2(v[8], v[9]);
+      q1.y = pack_bf16x2(v[10], v[11]);
+      q1.z = pack_bf16x2(v[12], v[13]);
+      q1.w = pack_bf16x2(v[14], v[15]);
+      reinterpret_cast<uint4*>(dst)[0] = q0;
+      reinterpret_cast<uint4*>(dst)[1] = q1;
+    } else {
+      for (int j = 0; j < ncols; j++) dst[j] = __float2bfloat16(v[j]);
+    }
+  } else {
+    float* dst = reinterpret_cast<float*>(p.out) + o;
+    if (ncols == 16 && p.vec_ok) {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      for (int j = 0; j < ncols; j++) dst[j] = v[j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 kernel
+// ------------------------------------------------------------------------------------------------
+struct TileCoord {
+  int img, y0, x0, n_tile;
+};
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
+  TileCoord t;
+  int m_tile = tile / p.n_tiles;
+  t.n_tile = tile - m_tile * p.n_tiles;
+  int per_img = p.tiles_y * p.tiles_x;
+  t.img = m_tile / per_img;
+  int r = m_tile - t.img * per_img;
+  int ty = r / p.tiles_x;
+  t.y0 = ty * p.TH;
+  t.x0 = (r - ty * p.tiles_x) * p.TW;
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                const __grid_constant__ CUtensorMap map_b, const __grid_constant__ IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full[2];
+  __shared__ __align__(8) uint64_t tmem_empty[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);   // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_b);
+    if (p.kchunks[1] > 0) tma_prefetch_desc(&map_a1);
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const uint32_t a_bytes = (uint32_t)(p.TH * p.TW) * 128u;
+  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TileCoord t = decode_tile(p, tile);
+        const int n0 = t.n_tile * p.BN;
+        for (int tap = 0; tap < p.taps; tap++) {
+          const int bz = p.w_batched ? t.img : tap;
+          for (int src = 0; src < 2; src++) {
+            const CUtensorMap* ma = src ? &map_a1 : &map_a0;
+            const int kb = src ? p.c1_off : 0;
+            for (int kc = 0; kc < p.kchunks[src]; kc++) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+              uint8_t* sb = sa + kABytes;
+              mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+              tma_load_5d(sa, ma, &full_bar[stage], p.tap_dc[tap] + kc * 64, t.x0 + p.tap_dx[tap], p.tap_dp[tap],
+                          t.y0 + p.tap_dy[tap], t.img);
+              tma_load_3d(sb, &map_b, &full_bar[stage], kb + kc * 64, n0, bz);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
+      const int kiters = p.taps * (p.kchunks[0] + p.kchunks[1]);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int ki = 0; ki < kiters; ki++) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint64_t da = umma_smem_desc(sa, 16, 1024);
+          const uint64_t db = umma_smem_desc(sa + kABytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            // +32 bytes (16 bf16) along K inside the 128B swizzle atom == +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (ki | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs have read it
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM lane quarter = warp % 4) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ry = row / p.TW, rx = row - ry * p.TW;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+      const int acc = it & 1;
+      TileCoord t = decode_tile(p, tile);
+      const int y = t.y0 + ry, x = t.x0 + rx;
+      const bool valid = (ry < p.TH) && (y < p.H) && (x < p.W);
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+      const int n0 = t.n_tile * p.BN;
+      if (p.epi_mode == EPI_PLAIN) {
+        for (int c = 0; c < p.BN; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c, r);
+          tmem_ld_wait();
+          if (valid) {
+            float a[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) a[j] = __uint_as_float(r[j]);
+            epilogue16(p, t.img, y, x, n0 + c, 0, n0 + c, a, a);
+          }
+        }
+      } else {
+        const int half = p.BN >> 1;
+        for (int c = 0; c < half; c += 16) {
+          uint32_t r0[16], r1[16];
+          tmem_ld16(taddr + c, r0);
+          tmem_ld16(taddr + half + c, r1);
+          tmem_ld_wait();
+          if (valid) {
+            float a[16], b[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              a[j] = __uint_as_float(r0[j]);
+              b[j] = __uint_as_float(r1[j]);
+            }
+            epilogue16(p, t.img, y, x, n0 + c, n0 + half + c, t.n_tile * half + c, a, b);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT checking kernel: one thread = one pixel x 16 output columns.  Debug / test use only.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void simt_dot16(const IgemmParams& p, int img, int y, int x, int gcol, float* acc) {
+#pragma unroll
+  for (int j = 0; j < 16; j++) acc[j] = 0.f;
+  const int taps = p.taps;
+  for (int tap = 0; tap < taps; tap++) {
+    int iy = y, ix = x;
+    if (p.ksize == 3) {
+      iy = y * p.stride + tap / 3 - 1;
+      ix = x * p.stride + tap % 3 - 1;
+    }
+    if (iy < 0 || iy >= p.h_in || ix < 0 || ix >= p.w_in) continue;
+    const long long ipix = ((long long)img * p.h_in + iy) * p.w_in + ix;
+    const __nv_bfloat16* wz = p.w_ptr + (long long)(p.w_batched ? img : tap) * p.w_z;
+    int kbase = 0;
+    for (int src = 0; src < 2; src++) {
+      const int C = p.a_c[src];
+      if (C == 0) continue;
+      const __nv_bfloat16* ap = p.a_ptr[src] + ipix * p.a_pix[src];
+      for (int c = 0; c < C; c++) {
+        const float av = __bfloat162float(ap[c]);
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          if (gcol + j < p.cout) acc[j] += av * __bfloat162float(wz[(long long)(gcol + j) * p.w_row + kbase + c]);
+        }
+      }
+      kbase += C;
+    }
+  }
+}
+
+__global__ void igemm_simt_kernel(const __grid_constant__ IgemmParams p) {
+  const int groups = (p.ncols_out + 15) / 16;
+  const long long total = (long long)p.n_img * p.H * p.W * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    long long pix = i / groups;
+    const int x = (int)(pix % p.W);
+    pix /= p.W;
+    const int y = (int)(pix % p.H);
+    const int img = (int)(pix / p.H);
+    const int ocol = g * 16;
+    float a[16], b[16];
+    if (p.epi_mode == EPI_PLAIN) {
+      simt_dot16(p, img, y, x, ocol, a);
+      epilogue16(p, img, y, x, ocol, 0, ocol, a, a);
+    } else {
+      const int half = p.BN >> 1;
+      const int nt = ocol / half, c = ocol - nt * half;
+      const int ga = nt * p.BN + c, gb = ga + half;
+      simt_dot16(p, img, y, x, ga, a);
+      simt_dot16(p, img, y, x, gb, b);
+      epilogue16(p, img, y, x, ga, gb, ocol, a, b);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &f, 12000, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+int make_tensor_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  ONEDC_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  cuuint64_t d[5], s[4];
+  cuuint32_t b[5];
+  for (int i = 0; i < rank; i++) {
+    d[i] = dims[i];
+    b[i] = box[i];
+  }
+  for (int i = 0; i + 1 < rank; i++) s[i] = strides_bytes[i];
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), d, s, b, ones,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] strides [%llu %llu %llu %llu] "
+              "box [%u %u %u %u %u] ptr %p",
+              (int)r, rank, (unsigned long long)d[0], (unsigned long long)(rank > 1 ? d[1] : 0),
+              (unsigned long long)(rank > 2 ? d[2] : 0), (unsigned long long)(rank > 3 ? d[3] : 0),
+              (unsigned long long)(rank > 4 ? d[4] : 0), (unsigned long long)s[0],
+              (unsigned long long)(rank > 2 ? s[1] : 0), (unsigned long long)(rank > 3 ? s[2] : 0),
+              (unsigned long long)(rank > 4 ? s[3] : 0), b[0], rank > 1 ? b[1] : 0, rank > 2 ? b[2] : 0,
+              rank > 3 ? b[3] : 0, rank > 4 ? b[4] : 0, ptr);
+    return -3;
+  }
+  return 0;
+}
+
+static int pick_bn(int cout, bool pair) {
+  const int step = pair ? 32 : 16;
+  if (cout <= 256) return ((cout + step - 1) / step) * step;
+  int best = 256, best_waste = 1 << 30;
+  for (int bn = 256; bn >= 96; bn -= step) {
+    int nt = (cout + bn - 1) / bn;
+    int waste = nt * bn - cout;
+    if (waste < best_waste) {
+      best_waste = waste;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+static void pick_tile(int H, int W, int* th, int* tw) {
+  if (H == 1) {
+    *th = 1;
+    *tw = 128;
+    return;
+  }
+  long long best = -1;
+  for (int t = 128; t >= 2; t >>= 1) {  // tw candidates 128..2
+    int h = 128 / t;
+    long long tiles = (long long)((H + h - 1) / h) * ((W + t - 1) / t);
+    if (best < 0 || tiles < best) {
+      best = tiles;
+      *th = h;
+      *tw = t;
+    }
+  }
+}
+
+static int igemm_launch(const onedc_igemm_desc* d, cudaStream_t stream) {
+  ONEDC_CHECK(d->ksize == 1 || d->ksize == 3, "igemm: ksize must be 1 or 3");
+  ONEDC_CHECK(d->stride == 1 || (d->stride == 2 && d->ksize == 3), "igemm: stride 2 needs ksize 3");
+  ONEDC_CHECK(d->a_c[0] > 0 && d->a_c[0] % 8 == 0 && d->a_c[1] % 8 == 0, "igemm: channels must be multiples of 8");
+  ONEDC_CHECK(d->a_pix_stride[0] % 8 == 0 && (d->a_c[1] == 0 || d->a_pix_stride[1] % 8 == 0),
+              "igemm: pixel strides must be multiples of 8 elements");
+  ONEDC_CHECK(d->ktot >= d->a_c[0] + d->a_c[1] && d->w_row_stride % 8 == 0 && d->w_z_stride % 8 == 0,
+              "igemm: bad weight strides");
+  const bool pair = d->epi_mode != EPI_PLAIN;
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_img = d->n_img;
+  p.h_in = d->h_in;
+  p.w_in = d->w_in;
+  p.ksize = d->ksize;
+  p.stride = d->stride;
+  if (d->stride == 2) {
+    ONEDC_CHECK(d->h_in % 2 == 0 && d->w_in % 2 == 0 && d->a_c[0] % 64 == 0 && d->a_c[1] == 0,
+                "igemm: stride-2 conv needs even dims, C %% 64 == 0 and a single source");
+    p.H = d->h_in / 2;
+    p.W = d->w_in / 2;
+  } else {
+    p.H = d->h_in;
+    p.W = d->w_in;
+  }
+  p.cout = d->cout;
+  p.BN = d->bn > 0 ? d->bn : pick_bn(d->cout, pair);
+  ONEDC_CHECK(p.BN >= 16 && p.BN <= 256 && p.BN % (pair ? 32 : 16) == 0, "igemm: bad BN %d", p.BN);
+  p.n_tiles = (d->cout + p.BN - 1) / p.BN;
+  if (pair) ONEDC_CHECK(d->cout % p.BN == 0, "igemm: pair epilogues need cout %% BN == 0 (cout %d BN %d)", d->cout, p.BN);
+  pick_tile(p.H, p.W, &p.TH, &p.TW);
+  p.tiles_y = (p.H + p.TH - 1) / p.TH;
+  p.tiles_x = (p.W + p.TW - 1) / p.TW;
+  p.m_tiles = p.n_img * p.tiles_y * p.tiles_x;
+  p.taps = d->ksize * d->ksize;
+  p.kchunks[0] = (d->a_c[0] + 63) / 64;
+  p.kchunks[1] = (d->a_c[1] + 63) / 64;
+  p.c1_off = d->a_c[0];
+  p.w_batched = d->w_batched;
+  ONEDC_CHECK(!(d->w_batched && p.taps != 1), "igemm: batched weights need a 1x1 kernel");
+  for (int t = 0; t < p.taps; t++) {
+    int ky = t / 3, kx = t % 3;
+    if (d->ksize == 1) {
+      p.tap_dc[t] = p.tap_dx[t] = p.tap_dp[t] = p.tap_dy[t] = 0;
+    } else if (d->stride == 1) {
+      p.tap_dc[t] = 0;
+      p.tap_dx[t] = kx - 1;
+      p.tap_dp[t] = 0;
+      p.tap_dy[t] = ky - 1;
+    } else {
+      const int px = (kx == 1) ? 0 : 1, py = (ky == 1) ? 0 : 1;
+      p.tap_dc[t] = px * (int)d->a_pix_stride[0];
+      p.tap_dx[t] = (kx == 0) ? -1 : 0;
+      p.tap_dp[t] = py;
+      p.tap_dy[t] = (ky == 0) ? -1 : 0;
+    }
+  }
+  p.stage_bytes = kABytes + ((p.BN * 128 + 1023) / 1024) * 1024;
+  p.stages = kSmemBudget / p.stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  p.bias = d->bias;
+  p.epi_mode = d->epi_mode;
+  p.act = d->act;
+  p.slope = d->slope;
+  p.res = d->res;
+  p.res_dtype = d->res_dtype;
+  p.res_ld = d->res_ld;
+  p.out = d->out;
+  p.out_dtype = d->out_dtype;
+  p.out_ld = d->out_ld;
+  p.out_col_off = d->out_col_off;
+  p.store_mode = d->store_mode;
+  p.ps_c = d->ps_c;
+  p.ncols_out = pair ? d->cout / 2 : d->cout;
+  if (d->store_mode == ST_PIXSHUF)
+    ONEDC_CHECK(d->ps_c > 0 && d->ps_c % 16 == 0 && p.ncols_out == 4 * d->ps_c && d->res == nullptr,
+                "igemm: pixel-shuffle store needs ncols == 4*ps_c, ps_c %% 16 == 0, no residual");
+  {
+    const int va = (d->out_dtype == DT_BF16) ? 8 : 4;
+    bool ok = (d->out_ld % va == 0) && (d->out_col_off % va == 0) &&
+              (reinterpret_cast<uintptr_t>(d->out) % 16 == 0) && d->store_mode != ST_TRANSPOSED;
+    if (d->res != nullptr)
+      ok = ok && (d->res_ld % 8 == 0) && (reinterpret_cast<uintptr_t>(d->res) % 16 == 0);
+    p.vec_ok = ok ? 1 : 0;
+  }
+  p.a_ptr[0] = reinterpret_cast<const __nv_bfloat16*>(d->a_ptr[0]);
+  p.a_ptr[1] = reinterpret_cast<const __nv_bfloat16*>(d->a_ptr[1]);
+  p.a_c[0] = d->a_c[0];
+  p.a_c[1] = d->a_c[1];
+  p.a_pix[0] = d->a_pix_stride[0];
+  p.a_pix[1] = d->a_pix_stride[1];
+  p.w_ptr = reinterpret_cast<const __nv_bfloat16*>(d->w_ptr);
+  p.ktot = d->ktot;
+  p.w_row = d->w_row_stride;
+  p.w_z = d->w_z_stride;
+
+  if (d->impl == 1) {
+    long long total = (long long)p.n_img * p.H * p.W * ((p.ncols_out + 15) / 16);
+    int blocks = (int)((total + 127) / 128);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    igemm_simt_kernel<<<blocks, 128, 0, stream>>>(p);
+    count_launch();
+    ONEDC_CUDA(cudaGetLastError());
+    return 0;
+  }
+
+  // ---- tensor maps
+  CUtensorMap ma[2], mb;
+  memset(ma, 0, sizeof(ma));
+  for (int s = 0; s < 2; s++) {
+    if (d->a_c[s] == 0) {
+      ma[s] = ma[0];
+      continue;
+    }
+    ONEDC_CHECK(reinterpret_cast<uintptr_t>(d->a_ptr[s]) % 16 == 0, "igemm: A pointer must be 16-byte aligned");
+    const uint64_t S = (uint64_t)d->a_pix_stride[s];
+    uint64_t dims[5], str[4];
+    uint32_t box[5] = {64, (uint32_t)p.TW, 1, (uint32_t)p.TH, 1};
+    if (d->stride == 1) {
+      dims[0] = (uint64_t)d->a_c[s];
+      dims[1] = (uint64_t)d->w_in;
+      dims[2] = 1;
+      dims[3] = (uint64_t)d->h_in;
+      dims[4] = (uint64_t)d->n_img;
+      str[0] = S * 2;
+      str[1] = (uint64_t)d->w_in * S * 2;
+      str[2] = (uint64_t)d->w_in * S * 2;
+      str[3] = (uint64_t)d->h_in * d->w_in * S * 2;
+    } else {
+      dims[0] = S + (uint64_t)d->a_c[s];
+      dims[1] = (uint64_t)d->w_in / 2;
+      dims[2] = 2;
+      dims[3] = (uint64_t)d->h_in / 2;
+      dims[4] = (uint64_t)d->n_img;
+      str[0] = 2 * S * 2;
+      str[1] = (uint64_t)d->w_in * S * 2;
+      str[2] = 2 * (uint64_t)d->w_in * S * 2;
+      str[3] = (uint64_t)d->h_in * d->w_in * S * 2;
+    }
+    int rc = make_tensor_map(&ma[s], d->a_ptr[s], 5, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    ONEDC_CHECK(reinterpret_cast<uintptr_t>(d->w_ptr) % 16 == 0, "igemm: W pointer must be 16-byte aligned");
+    const int nz = d->w_batched ? d->n_img : p.taps;
+    uint64_t dims[3] = {(uint64_t)d->ktot, (uint64_t)d->cout, (uint64_t)nz};
+    uint64_t str[2] = {(uint64_t)d->w_row_stride * 2, (uint64_t)d->w_z_stride * 2};
+    if (nz == 1) str[1] = str[0] * dims[1];
+    uint32_t box[3] = {64, (uint32_t)p.BN, 1};
+    int rc = make_tensor_map(&mb, d->w_ptr, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  int grid = total_tiles < sm_count() ? total_tiles : sm_count();
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ONEDC_CUDA(cudaFuncSetAttribute(igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBudget + 1024));
+    attr_set = true;
+  }
+  igemm_tc_kernel<<<grid, kThreads, smem, stream>>>(ma[0], ma[1], mb, p);
+  count_launch();
+  ONEDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace onedc
+
+extern "C" int onedc_igemm(const onedc_igemm_desc* d, void* stream) {
+  return onedc::igemm_launch(d, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,329 @@
+"""Python-side wrappers of the C-ABI kernels: torch tensors in (device memory + current stream only),
+kernels of libonedc_b200.so do all the math.  Activations are NHWC bf16 tensors [N, H, W, C]; channel
+slices of a wider buffer (x[..., a:b]) are passed as views, never copied.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import lib as L
+from .lib import (ACT_GELU, ACT_LRELU, ACT_NONE, ACT_SILU, BF16, EPI_GEGLU, EPI_PAIR_LRELU, EPI_PLAIN, F32,
+                  ST_NORMAL, ST_PIXSHUF, ST_TRANSPOSED)
+
+# 0 = tcgen05 kernels (product).  1 = SIMT checking kernels; tests flip this to cross-check on the GPU.
+IMPL = int(os.environ.get("ONEDC_IMPL", "0"))
+# attention route: "flash" = onedc_attention; "unfused" = batched GEMM + softmax + GEMM (tests only)
+ATTN = os.environ.get("ONEDC_ATTN", "flash")
+# when set to a list, igemm/attention append (name, start_event, end_event, algorithmic_flops) per launch
+PROFILE = None
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _prof_end(name, e0, flops):
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        PROFILE.append((name, e0, e1, flops))
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dt(t):
+    if t.dtype == torch.bfloat16:
+        return BF16
+    if t.dtype == torch.float32:
+        return F32
+    raise TypeError(t.dtype)
+
+
+def _nhwc(t):
+    """(ptr, n, h, w, c, pix_stride) of an NHWC view whose pixels are laid out densely in (n, h, w)."""
+    if t.dim() == 3:
+        t = t.unsqueeze(1)
+    n, h, w, c = t.shape
+    ps = t.stride(2) if w > 1 else (t.stride(1) if h > 1 else (t.stride(0) if n > 1 else c))
+    assert t.stride(3) == 1, "channels must be contiguous"
+    if w > 1:
+        assert h == 1 or t.stride(1) == w * ps, "rows must be dense"
+    if n > 1:
+        assert t.stride(0) == h * w * ps, f"images must be dense {t.shape} {t.stride()}"
+    return t.data_ptr(), n, h, w, c, ps
+
+
+class ConvW:
+    """Kernel-layout weights of one conv / linear: bf16 [taps, cout, ktot] + fp32 bias."""
+
+    def __init__(self, w, bias=None, device="cuda", epi=EPI_PLAIN, bn=0):
+        # w: fp32 [cout, cin, k, k] or [cout, cin]
+        if w.dim() == 2:
+            w = w[:, :, None, None]
+        cout, cin, k, _ = w.shape
+        pad = (-cin) % 8
+        if pad:
+            w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, pad))
+        self.ksize, self.cout, self.ktot = k, cout, cin + pad
+        self.w = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin + pad).contiguous().to(device=device, dtype=torch.bfloat16)
+        self.bias = None if bias is None else bias.detach().float().contiguous().to(device)
+        self.epi, self.bn = epi, bn
+        self.ncols = cout // 2 if epi != EPI_PLAIN else cout
+
+
+def pair_permute(w, b, bn=256):
+    """Reorders output channels so that every N tile of `bn` GEMM columns holds bn/2 channels of the first
+    half followed by the matching bn/2 channels of the second half (ConvFFN3 / GEGLU epilogues)."""
+    cout = w.shape[0]
+    half, hb = cout // 2, bn // 2
+    assert cout % bn == 0
+    idx = []
+    for t in range(cout // bn):
+        idx += list(range(t * hb, (t + 1) * hb)) + list(range(half + t * hb, half + (t + 1) * hb))
+    idx = torch.tensor(idx)
+    return w[idx], (None if b is None else b[idx])
+
+
+def pixshuf_permute(w, b):
+    """PixelShuffle(2): original row 4c + q  ->  row q*C + c, so each quarter of the GEMM columns is one
+    sub-pixel position holding C contiguous channels."""
+    cout = w.shape[0]
+    c = cout // 4
+    idx = torch.arange(cout).reshape(c, 4).t().reshape(-1)
+    return w[idx], (None if b is None else b[idx])
+
+
+def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None, out_dtype=torch.bfloat16,
+          store=ST_NORMAL, ps_c=0, w_batched=False, impl=None):
+    """out = epilogue(conv(x [cat x2], wt)).  `out` may be a channel-slice view of a wider buffer."""
+    lib = L.load()
+    d = L.IgemmDesc()
+    p0, n, h, w, c0, s0 = _nhwc(x)
+    d.a_ptr[0], d.a_c[0], d.a_pix_stride[0] = p0, c0, s0
+    if x2 is not None:
+        p1, n1, h1, w1, c1, s1 = _nhwc(x2)
+        assert (n1, h1, w1) == (n, h, w)
+        d.a_ptr[1], d.a_c[1], d.a_pix_stride[1] = p1, c1, s1
+    else:
+        c1 = 0
+    d.n_img, d.h_in, d.w_in = n, h, w
+    if isinstance(wt, ConvW):
+        assert wt.ktot >= c0 + c1, f"weight K {wt.ktot} < channels {c0}+{c1}"
+        d.ksize, d.w_ptr, d.cout, d.ktot = wt.ksize, wt.w.data_ptr(), wt.cout, wt.ktot
+        d.w_row_stride, d.w_z_stride = wt.ktot, wt.cout * wt.ktot
+        d.bias = None if wt.bias is None else wt.bias.data_ptr()
+        d.epi_mode, d.bn = wt.epi, wt.bn
+        ncols = wt.ncols
+    else:                                   # (tensor [z, rows, k] view, ...) used as a batched B operand
+        bt = wt
+        assert bt.dim() == 3 and bt.stride(2) == 1
+        d.ksize, d.w_ptr, d.cout, d.ktot = 1, bt.data_ptr(), bt.shape[1], bt.shape[2]
+        d.w_row_stride, d.w_z_stride = bt.stride(1), bt.stride(0)
+        d.bias, d.epi_mode, d.bn = None, EPI_PLAIN, 0
+        ncols = bt.shape[1]
+    d.stride, d.w_batched = stride, 1 if w_batched else 0
+    d.act, d.slope = act, slope
+    ho, wo = (h // 2, w // 2) if stride == 2 else (h, w)
+    if out is None:
+        if store == ST_PIXSHUF:
+            out = torch.empty((n, 2 * ho, 2 * wo, ps_c), device=x.device, dtype=out_dtype)
+        elif store == ST_TRANSPOSED:
+            out = torch.empty((n, ncols, ho * wo), device=x.device, dtype=out_dtype)
+        else:
+            out = torch.empty((n, ho, wo, ncols), device=x.device, dtype=out_dtype)
+    if store == ST_TRANSPOSED:
+        assert out.stride(2) == 1 and out.stride(0) == ncols * out.stride(1)
+        d.out, d.out_ld, d.out_col_off = out.data_ptr(), out.stride(1), 0
+    else:
+        po, no, hoo, woo, co, so = _nhwc(out)
+        d.out, d.out_ld, d.out_col_off = po, so, 0
+    d.out_dtype, d.store_mode, d.ps_c = _dt(out), store, ps_c
+    if res is not None:
+        pr, _, _, _, cr, sr = _nhwc(res)
+        d.res, d.res_dtype, d.res_ld = pr, _dt(res), sr
+    d.impl = IMPL if impl is None else impl
+    e0 = _prof_begin()
+    L.check(lib.onedc_igemm(C.byref(d), _stream()), "onedc_igemm")
+    _prof_end("igemm", e0, 2.0 * n * ho * wo * d.cout * (c0 + c1) * d.ksize * d.ksize)
+    return out
+
+
+def attention(q, k, v, out, heads, head_dim, scale=None, impl=None):
+    """q [B,Sq,*], k/v [B,Skv,*] channel-slice views (head h at columns h*d), out [B,Sq,heads*d] view."""
+    lib = L.load()
+    b, sq, _ = q.shape
+    skv = k.shape[1]
+    assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1 and out.stride(2) == 1
+    assert k.stride(1) == v.stride(1)
+    assert b == 1 or (q.stride(0) == sq * q.stride(1) and k.stride(0) == skv * k.stride(1)
+                      and v.stride(0) == skv * v.stride(1) and out.stride(0) == sq * out.stride(1))
+    scale = head_dim ** -0.5 if scale is None else scale
+    e0 = _prof_begin()
+    L.check(lib.onedc_attention(q.data_ptr(), q.stride(1), k.data_ptr(), v.data_ptr(), k.stride(1), out.data_ptr(),
+                                out.stride(1), b, heads, head_dim, sq, skv, scale, IMPL if impl is None else impl,
+                                _stream()), "onedc_attention")
+    _prof_end("attention", e0, 4.0 * b * heads * sq * skv * head_dim)
+    return out
+
+
+def attention_unfused(q, k, vT, out, heads, head_dim, scale=None, valid=None):
+    """softmax(q k^T) v through batched GEMMs with the score matrix materialised (short sequences / big
+    head dims: SemanticAdaptor AttnBlock, VAE windowed mid-block attention).
+    q, k: [B, S, *] views; vT: [B, heads*d, Lpad] (V transposed, zero beyond L); valid: optional int32 [B]."""
+    lib = L.load()
+    b, sq, _ = q.shape
+    skv, lpad = k.shape[1], vT.shape[2]
+    scale = head_dim ** -0.5 if scale is None else scale
+    scores = torch.empty((b, 1, sq, lpad), device=q.device, dtype=torch.float32)
+    probs = torch.empty((b, 1, sq, lpad), device=q.device, dtype=torch.bfloat16)
+    for h in range(heads):
+        sl = slice(h * head_dim, (h + 1) * head_dim)
+        igemm(q[:, None, :, sl], k[:, :, sl], out=scores[..., :skv], w_batched=True)
+        if valid is None:
+            L.check(lib.onedc_softmax_rows(scores.data_ptr(), lpad, b * sq, lpad, skv, scale, probs.data_ptr(), lpad,
+                                           _stream()), "softmax")
+        else:
+            L.check(lib.onedc_softmax_rows_batched(scores.data_ptr(), lpad, b * sq, lpad, valid.data_ptr(), sq, scale,
+                                                   probs.data_ptr(), lpad, _stream()), "softmax")
+        igemm(probs, vT[:, sl, :], out=out[:, None, :, sl], w_batched=True)
+    return out
+
+
+class GroupNorm:
+    def __init__(self, gamma, beta, eps, groups=32, device="cuda"):
+        self.gamma = gamma.detach().float().contiguous().to(device)
+        self.beta = beta.detach().float().contiguous().to(device)
+        self.eps, self.groups = eps, groups
+
+    def __call__(self, x, x2=None, silu=True, out=None):
+        lib = L.load()
+        p0, n, h, w, c0, s0 = _nhwc(x)
+        p1, c1, s1 = 0, 0, 0
+        if x2 is not None:
+            p1, _, _, _, c1, s1 = _nhwc(x2)
+        hw, ct = h * w, c0 + c1
+        ws = torch.empty(int(lib.onedc_groupnorm_ws_floats(n, hw, ct)), device=x.device, dtype=torch.float32)
+        stats = torch.empty((n, self.groups, 2), device=x.device, dtype=torch.float32)
+        L.check(lib.onedc_groupnorm_stats(p0, c0, s0, p1, c1, s1, _dt(x), n, hw, self.groups, self.eps,
+                                          ws.data_ptr(), stats.data_ptr(), _stream()), "groupnorm_stats")
+        if out is None:
+            out = torch.empty((n, h, w, ct) if x.dim() == 4 else (n, hw, ct), device=x.device, dtype=torch.bfloat16)
+        po, _, _, _, _, so = _nhwc(out)
+        L.check(lib.onedc_groupnorm_apply(p0, c0, s0, p1, c1, s1, _dt(x), n, hw, self.groups, stats.data_ptr(),
+                                          self.gamma.data_ptr(), self.beta.data_ptr(), 1 if silu else 0, po, so,
+                                          _stream()), "groupnorm_apply")
+        return out
+
+
+class LayerNorm:
+    def __init__(self, gamma, beta, eps=1e-5, device="cuda"):
+        self.gamma = gamma.detach().float().contiguous().to(device)
+        self.beta = beta.detach().float().contiguous().to(device)
+        self.eps = eps
+
+    def __call__(self, x):
+        lib = L.load()
+        b, s, c = x.shape
+        assert x.is_contiguous()
+        out = torch.empty_like(x)
+        L.check(lib.onedc_layernorm(x.data_ptr(), c, b * s, c, self.gamma.data_ptr(), self.beta.data_ptr(), self.eps,
+                                    out.data_ptr(), c, _stream()), "layernorm")
+        return out
+
+
+class DepthwiseW:
+    def __init__(self, w, b, device="cuda"):
+        c = w.shape[0]
+        self.c = c
+        self.w = w.reshape(c, 9).t().contiguous().float().to(device)       # [9][C]
+        self.b = b.detach().float().contiguous().to(device)
+
+
+def dwconv3x3(x, dw):
+    assert x.is_contiguous()
+    n, h, w, c = x.shape
+    out = torch.empty_like(x)
+    L.check(L.load().onedc_dwconv3x3(x.data_ptr(), dw.w.data_ptr(), dw.b.data_ptr(), out.data_ptr(), n, h, w, c,
+                                     _stream()), "dwconv3x3")
+    return out
+
+
+def upsample2x(x):
+    assert x.is_contiguous()
+    n, h, w, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=x.dtype)
+    L.check(L.load().onedc_upsample2x(x.data_ptr(), out.data_ptr(), n, h, w, c, _stream()), "upsample2x")
+    return out
+
+
+def window_partition(x, win):
+    assert x.is_contiguous()
+    n, h, w, c = x.shape
+    nw = ((h + win - 1) // win) * ((w + win - 1) // win)
+    out = torch.empty((n * nw, win * win, c), device=x.device, dtype=x.dtype)
+    L.check(L.load().onedc_window_partition(x.data_ptr(), out.data_ptr(), n, h, w, c, win, _stream()), "window_partition")
+    return out
+
+
+def window_merge(a, residual, win):
+    n, h, w, c = residual.shape
+    out = torch.empty_like(residual)
+    L.check(L.load().onedc_window_merge(a.data_ptr(), residual.data_ptr(), out.data_ptr(), n, h, w, c, win, _stream()),
+            "window_merge")
+    return out
+
+
+def x0_prepare(reduced, eps, sqrt_alpha, sqrt_1m_alpha, inv_scaling, pq_w, pq_b, want_x0=False):
+    """reduced/eps: fp32 NHWC [N,H,W,4].  Returns bf16 [N,H,W,8] = [hi(4) | lo(4)] of the post_quant_conv output."""
+    n, h, w, c = reduced.shape
+    assert c == 4 and reduced.is_contiguous() and eps.is_contiguous()
+    out = torch.empty((n, h, w, 8), device=reduced.device, dtype=torch.bfloat16)
+    x0 = torch.empty_like(reduced) if want_x0 else None
+    wv = (C.c_float * 16)(*[float(v) for v in pq_w.reshape(-1)])
+    bv = (C.c_float * 4)(*[float(v) for v in pq_b.reshape(-1)])
+    L.check(L.load().onedc_x0_prepare(reduced.data_ptr(), eps.data_ptr(), sqrt_alpha, sqrt_1m_alpha, inv_scaling,
+                                      C.cast(wv, C.c_void_p), C.cast(bv, C.c_void_p), out.data_ptr(),
+                                      0 if x0 is None else x0.data_ptr(), n * h * w, _stream()), "x0_prepare")
+    return out, x0
+
+
+def scale_to_index(scales, lut, step, idx_out=None):
+    p, n, h, w, c, s = _nhwc(scales)
+    assert c == 128
+    if idx_out is None:
+        idx_out = torch.empty((n, 32, h, w), device=scales.device, dtype=torch.int16)
+    L.check(L.load().onedc_scale_to_index(p, s, lut.data_ptr(), idx_out.data_ptr(), step, n, h, w, 32, _stream()),
+            "scale_to_index")
+    return idx_out
+
+
+def dequant_accum(sym, means, y_hat, step):
+    pm, n, h, w, c, sm = _nhwc(means)
+    py, _, _, _, _, sy = _nhwc(y_hat)
+    L.check(L.load().onedc_dequant_accum(0 if sym is None else sym.data_ptr(), pm, sm, py, sy, step, n, h, w, 32,
+                                         _stream()), "dequant_accum")
+    return y_hat
+
+
+def quantize_residual(y, means, sym, y_hat, step):
+    pyi, n, h, w, c, syi = _nhwc(y)
+    pm, _, _, _, _, sm = _nhwc(means)
+    py, _, _, _, _, sy = _nhwc(y_hat)
+    L.check(L.load().onedc_quantize_residual(pyi, syi, pm, sm, sym.data_ptr(), py, sy, step, n, h, w, 32, _stream()),
+            "quantize_residual")
+    return sym
+
+
+def fsq_codes(idx):
+    """int32 [N,hz,wz] -> bf16 NHWC [N,hz,wz,8]"""
+    n, h, w = idx.shape
+    out = torch.empty((n, h, w, 8), device=idx.device, dtype=torch.bfloat16)
+    L.check(L.load().onedc_fsq_codes(idx.data_ptr(), out.data_ptr(), n * h * w, _stream()), "fsq_codes")
+    return out

@@ -1,0 +1,273 @@
+"""CPU-side tests (no GPU): oracle pinned to the golden vectors made from the reference, the product's host
+logic (rANS coder, CDF/index tables, wire format, weight inventory, sharding) against the oracle and the golden
+vectors, and the C-ABI library's exported symbols."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from onedc_b200 import build, lib as L
+    build.build()
+    return L.load()
+
+
+# ----------------------------------------------------------------------------- oracle vs golden (reference) vectors
+def test_oracle_cdf_table_matches_reference_golden():
+    from oracle import entropy as E
+    g = np.load(os.path.join(GOLD, "cdf_table.npz"))
+    cdf, length, offset = E.gaussian_cdf_table()
+    assert np.array_equal(cdf, g["cdf"]) and np.array_equal(length, g["length"]) and np.array_equal(offset, g["offset"])
+    assert length.min() == 7 and length.max() == 103 and offset.min() == -50 and offset.max() == -2
+
+
+def test_oracle_index_lut_matches_reference_golden():
+    from oracle import entropy as E
+    lut = E.bf16_index_lut()
+    assert np.array_equal(lut, np.load(os.path.join(GOLD, "bf16_index_lut.npy")))
+    assert len(np.unique(lut)) == 256
+    first = int(np.argmax(lut[: 0x7F80] > 0))               # first positive bf16 with a non-zero index
+    assert torch.tensor([first << 16], dtype=torch.int32).view(torch.float32).item() == 0.11279296875
+
+
+def test_oracle_pmf_to_quantized_cdf_kat():
+    from oracle import entropy as E
+    assert E.pmf_to_quantized_cdf([.1, .2, .3, .4], 16).tolist() == [0, 6554, 19661, 39322, 65536]
+
+
+def test_oracle_decodes_reference_golden_stream():
+    """The reference IntraNoAR decoded this stream in gen_golden.py; the oracle must reproduce it."""
+    from onedc_b200 import weights as W
+    from oracle.decode import CodecOracle
+    g = np.load(os.path.join(GOLD, "codec_128x128.npz"))
+    orc = CodecOracle(W.random_state_dict(W.codec_spec(), 0))
+    trace = []
+    x_hat, y_sem, hw, phw, pad = orc.decode(g["stream"].tobytes(), trace)
+    assert hw == (128, 128) and phw == (128, 128) and pad == (0, 0, 0, 0)
+    for k in range(4):
+        assert np.array_equal(trace[k]["idx"].reshape(-1).numpy().astype(np.int16), g["idx"][k]), f"indices step {k}"
+        assert np.array_equal(trace[k]["sym"], g["sym"][k]), f"symbols step {k}"
+    assert np.allclose(trace[3]["y_hat"].numpy(), g["y_hat"], atol=1e-5)
+    assert np.abs(x_hat.numpy() - g["x_hat"].astype(np.float32)).max() < 2e-3      # golden stored as fp16
+    assert np.allclose(y_sem.numpy(), g["y_sem"], atol=1e-4)
+
+
+def test_oracle_rans_matches_reference_golden_bytes():
+    from oracle import entropy as E
+    g = np.load(os.path.join(GOLD, "rans_escape.npz"))
+    r = E.RansOracle()
+    assert r.encode([(g["sym"], g["idx"])]) == g["stream"].tobytes()
+    r.set_stream(g["stream"].tobytes())
+    assert np.array_equal(r.decode(g["idx"]), g["sym"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree only exists in the build container")
+def test_oracle_pinned_against_live_reference():
+    """Bit-exact comparison with the reference imported unchanged (fresh stream, other size/seed than the golden)."""
+    from onedc_b200 import weights as W
+    from oracle.decode import CodecOracle
+    from oracle.ref_import import build_reference_codec, reference_available
+    if not reference_available():
+        pytest.skip("oracle/_ref not built")
+    sd = W.random_state_dict(W.codec_spec(), 1)
+    ref = build_reference_codec()
+    ref.load_state_dict(sd, strict=False)
+    orc = CodecOracle(sd)
+    stream, z_idx, _ = orc.make_stream(64, 192, seed=77)
+    x_hat, y_sem, *_ = orc.decode(stream)
+    rx, rs, *_ = ref.decode(stream=stream)
+    assert torch.equal(x_hat, rx) and torch.equal(y_sem, rs)
+
+
+# ----------------------------------------------------------------------------- C ABI
+def test_library_exports_every_declared_symbol(lib):
+    from onedc_b200 import lib as L
+    hdr = open(os.path.join(ROOT, "include", "onedc_b200.h")).read()
+    body = hdr[hdr.index("const char* onedc_last_error"):]
+    declared = set(re.findall(r"\b(onedc_[a-z0-9_]+)\s*\(", body))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/onedc_b200.h but not exported"
+    assert declared == set(L.PROTOTYPES), f"header/binding mismatch: {declared ^ set(L.PROTOTYPES)}"
+    assert lib.onedc_version() >= 100
+
+
+# ----------------------------------------------------------------------------- product host logic vs oracle / golden
+def test_product_tables_match_golden(lib):
+    from onedc_b200.entropy_models import EntropyCoder, GaussianEncoder
+    ge = GaussianEncoder()
+    ge.update(force=True, entropy_coder=EntropyCoder())
+    g = np.load(os.path.join(GOLD, "cdf_table.npz"))
+    q, l, o = ge.get_cdf_info()
+    assert np.array_equal(q, g["cdf"]) and np.array_equal(l, g["length"]) and np.array_equal(o, g["offset"])
+    assert np.array_equal(ge._lut_host.numpy(), np.load(os.path.join(GOLD, "bf16_index_lut.npy")))
+    thr = ge._thr_host
+    assert thr.shape == (255,) and bool((thr[1:] > thr[:-1]).all())
+    from oracle import entropy as E
+    below = torch.nextafter(thr, torch.zeros_like(thr))
+    assert torch.equal(E.build_indexes(thr), torch.arange(1, 256, dtype=torch.int32))
+    assert torch.equal(E.build_indexes(below), torch.arange(0, 255, dtype=torch.int32))
+    assert EntropyCoder.pmf_to_quantized_cdf([.1, .2, .3, .4], 16).tolist() == [0, 6554, 19661, 39322, 65536]
+
+
+def test_product_rans_matches_oracle_and_golden(lib):
+    from onedc_b200.entropy_models import EntropyCoder, GaussianEncoder
+    from oracle import entropy as E
+    ec = EntropyCoder()
+    ge = GaussianEncoder()
+    ge.update(force=True, entropy_coder=ec)
+    g = np.load(os.path.join(GOLD, "rans_escape.npz"))
+    ec.reset()
+    ec.encode_with_indexes_np(g["sym"], g["idx"], 0)
+    ec.flush()
+    assert ec.get_encoded_stream() == g["stream"].tobytes(), "product encoder bytes != reference bytes"
+    ec.set_stream(g["stream"].tobytes())
+    assert np.array_equal(ec.decode_stream_np(g["idx"], 0), g["sym"])
+    # multi-call cursor + random data against the oracle C coder, including tiny and escape-heavy streams
+    rng = np.random.default_rng(1)
+    orc = E.RansOracle()
+    for n, wide in ((1, False), (7, True), (5000, False), (30000, True)):
+        idx = rng.integers(0, 256, n).astype(np.int16)
+        sc = np.exp(np.linspace(np.log(0.11), np.log(64), 256))[idx] * (4.0 if wide else 1.0)
+        sym = np.clip(np.rint(rng.standard_normal(n) * sc), -3000, 3000).astype(np.int16)
+        parts = np.array_split(np.arange(n), 4)
+        ec.reset()
+        for p in parts:
+            ec.encode_with_indexes_np(sym[p], idx[p], 0)
+        ec.flush()
+        data = ec.get_encoded_stream()
+        assert data == orc.encode([(sym[p], idx[p]) for p in parts])
+        ec.set_stream(data)
+        got = np.concatenate([ec.decode_stream_np(idx[p], 0) for p in parts]) if n > 3 else ec.decode_stream_np(idx, 0)
+        assert np.array_equal(got, sym)
+    with pytest.raises(Exception):
+        ec.set_stream(b"\x01\x00")                               # too short to hold a rANS state
+
+
+def test_product_golden_stream_symbols(lib):
+    """Host rANS of the product decodes the reference-made golden stream to the reference's symbols."""
+    from onedc_b200 import bitstream
+    from onedc_b200.entropy_models import EntropyCoder, GaussianEncoder, StreamDecoder
+    g = np.load(os.path.join(GOLD, "codec_128x128.npz"))
+    ec = EntropyCoder()
+    ge = GaussianEncoder()
+    ge.update(force=True, entropy_coder=ec)
+    d = bitstream.decode_i(g["stream"].tobytes())
+    assert np.array_equal(bitstream.unpack_indices(d["bit_stream_z"], 4), g["z_idx"].reshape(-1))
+    sd = StreamDecoder(ec, d["bit_stream_y"])
+    for k in range(4):
+        idx = np.ascontiguousarray(g["idx"][k])
+        out = np.empty_like(idx)
+        sd.decode_into(idx.ctypes.data, len(idx), out.ctypes.data)
+        assert np.array_equal(out, g["sym"][k])
+
+
+def test_bitstream_matches_oracle():
+    from onedc_b200 import bitstream
+    from oracle import entropy as E
+    rng = np.random.default_rng(3)
+    for (h, w) in ((768, 768), (100, 70), (64, 64), (2048, 2048), (1, 1)):
+        pl, pr, pt, pb = bitstream.get_padding_size(h, w)
+        assert (pl, pr, pt, pb) == E.padding_size(h, w)
+        cnt = ((h + pb) // 64) * ((w + pr) // 64)
+        idx = rng.integers(0, 16384, cnt)
+        z = bitstream.pack_indices(idx)
+        assert z == E.pack_z_indices(idx) and len(z) == (cnt * 14 + 7) // 8
+        assert np.array_equal(bitstream.unpack_indices(z, cnt), idx)
+        assert np.array_equal(E.unpack_z_indices(z, cnt), idx)
+        y = rng.integers(0, 256, 57).astype(np.uint8).tobytes()
+        s = bitstream.encode_i(h, w, y, z, b"", 0)
+        assert s == E.encode_container(h, w, y, z)
+        d, do = bitstream.decode_i(s), E.decode_container(s)
+        for k in ("height", "width", "pad_height", "pad_width", "pad_tuple", "bit_stream_y", "bit_stream_z"):
+            assert d[k] == do[k]
+    assert bitstream.pack_indices([0, 0]) == b"\x00" * 4 and bitstream.pack_indices([16383]) == b"\x3f\xff"
+    with pytest.raises(ValueError):
+        bitstream.decode_i(b"\x00" * 8)
+    with pytest.raises(ValueError):
+        bitstream.decode_i(s[:-5])
+
+
+def test_weight_inventory_matches_reference_keys():
+    from onedc_b200 import weights as W
+    spec = W.codec_spec()
+    mine = {n: "x".join(str(s) for s in shp) for n, shp, _, _ in spec}
+    gold = dict(line.split() for line in open(os.path.join(GOLD, "codec_keys.txt")) if line.strip())
+    assert mine == gold
+    assert abs(sum(int(np.prod(s)) for _, s, _, _ in spec) / 1e6 - 80.2) < 0.1
+    # oracle modules accept the inventories with strict=True (names, shapes) -- UNet / VAE included
+    from oracle.nets import UNetOracle, VAEOracle
+    with torch.device("meta"):
+        u, v = UNetOracle(), VAEOracle()
+    us, vs = W.unet_spec(), W.vae_spec()
+    assert {n: tuple(s) for n, s, _, _ in us} == {k: tuple(p.shape) for k, p in u.state_dict().items()}
+    assert {n: tuple(s) for n, s, _, _ in vs} == {k: tuple(p.shape) for k, p in v.state_dict().items()}
+    base = sum(int(np.prod(s)) for n, s, k, _ in us if k != "lora")
+    assert 855e6 < base < 870e6, base                      # SD1.5 UNet ~ 860 M params
+    sd = W.random_state_dict(us[:8], 0)
+    w, b = W.merge_lora({**sd}, "time_embedding.linear_1")
+    assert w.shape == (1280, 320)
+
+
+def test_lora_merge_equals_side_branch():
+    from onedc_b200 import weights as W
+    from oracle.nets import LoraConv2d, LoraLinear
+    g = torch.Generator().manual_seed(0)
+    for mod, name, x in ((LoraConv2d(16, 24, 3, padding=1), "c", torch.randn(1, 16, 8, 8, generator=g)),
+                         (LoraLinear(32, 48), "l", torch.randn(5, 32, generator=g))):
+        for p in mod.parameters():
+            torch.nn.init.normal_(p, std=0.1, generator=g)
+        sd = {f"{name}.{k}": v for k, v in mod.state_dict().items()}
+        w, b = W.merge_lora(sd, name)
+        y = torch.nn.functional.conv2d(x, w, b, padding=1) if w.dim() == 4 else torch.nn.functional.linear(x, w, b)
+        assert torch.allclose(y, mod(x), atol=1e-5)
+
+
+def test_no_product_import_of_oracle():
+    """The product package must never import/call oracle/ (it is the checker)."""
+    for root, _, files in os.walk(os.path.join(ROOT, "onedc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports oracle"
+                assert "oracle/" not in src.replace("checker", ""), f"{f} references oracle/"
+
+
+# ----------------------------------------------------------------------------- multi-process sharding (gloo, world 2)
+_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, %r)
+import torch
+from onedc_b200 import parallel as P
+rank, world, local = P.init_distributed("gloo")
+items = list(range(13))
+mine = P.shard(items, rank, world)
+P.barrier()
+t = P.reduce_max(1.0 + rank)
+n = P.reduce_sum(len(mine))
+print(json.dumps({"rank": rank, "mine": mine, "tmax": t, "total": n}))
+'''
+
+
+def test_sharding_world2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER % ROOT)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    import json
+    res = [json.loads(o.strip().splitlines()[-1]) for o in outs]
+    assert sorted(res[0]["mine"] + res[1]["mine"]) == list(range(13))
+    assert not set(res[0]["mine"]) & set(res[1]["mine"])
+    assert all(r["tmax"] == 2.0 and r["total"] == 13 for r in res)

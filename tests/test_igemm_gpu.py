@@ -1,0 +1,154 @@
+"""GPU parity of the tcgen05 implicit-GEMM kernel (through the C ABI) against fp32 PyTorch convolutions of the
+same bf16-rounded operands, and against the library's SIMT checking kernel."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, dev, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).to(dev)
+
+
+def _ref_conv(x, w, b, k, stride, x2=None):
+    xs = x.float() if x2 is None else torch.cat([x.float(), x2.float()], dim=-1)
+    y = F.conv2d(xs.permute(0, 3, 1, 2), w, b, stride=stride, padding=k // 2)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def _close(a, b, tol=1.5e-2):
+    a, b = a.float(), b.float()
+    scale = b.abs().max().clamp_min(1e-6)
+    err = (a - b).abs().max() / scale
+    assert err < tol, f"max rel-to-peak error {err.item():.4g}"
+
+
+CASES = [
+    # n, h, w, cin, cout, k, stride
+    (1, 1, 200, 64, 64, 1, 1),
+    (1, 1, 128, 128, 256, 1, 1),
+    (2, 12, 12, 128, 128, 1, 1),
+    (1, 16, 16, 320, 320, 3, 1),
+    (1, 24, 20, 64, 48, 3, 1),
+    (2, 16, 16, 128, 640, 3, 1),
+    (1, 32, 32, 256, 128, 3, 1),
+    (1, 16, 16, 320, 320, 3, 2),
+    (1, 8, 8, 1280, 1280, 3, 2),
+    (1, 4, 4, 8, 128, 1, 1),
+    (1, 32, 32, 8, 512, 3, 1),
+    (1, 32, 32, 320, 4, 3, 1),
+    (1, 48, 48, 512, 2048, 1, 1),
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k,stride", CASES)
+@pytest.mark.parametrize("impl", [0, 1])
+def test_conv_matches_torch(cuda, n, h, w, cin, cout, k, stride, impl):
+    from onedc_b200 import ops
+    x = _mk((n, h, w, cin), cuda, 1)
+    wt = _mk((cout, cin, k, k), "cpu", 2, scale=(cin * k * k) ** -0.5).float()
+    b = _mk((cout,), "cpu", 3).float()
+    cw = ops.ConvW(wt, b, cuda)
+    out = ops.igemm(x, cw, stride=stride, impl=impl)
+    ref = _ref_conv(x, cw.w.float().reshape(k, k, cout, -1).permute(2, 3, 0, 1)[:, :cin].contiguous(), b.to(cuda), k, stride)
+    assert out.shape == ref.shape
+    _close(out, ref)
+
+
+def test_two_sources_residual_act_fp32(cuda):
+    from onedc_b200 import ops
+    n, h, w = 1, 24, 24
+    x, x2 = _mk((n, h, w, 320), cuda, 1), _mk((n, h, w, 640), cuda, 2)
+    wt = _mk((320, 960, 3, 3), "cpu", 3, scale=(960 * 9) ** -0.5).float()
+    b = _mk((320,), "cpu", 4).float()
+    res = _mk((n, h, w, 320), cuda, 5)
+    cw = ops.ConvW(wt, b, cuda)
+    for impl in (0, 1):
+        out = ops.igemm(x, cw, x2=x2, act=ops.ACT_LRELU, slope=0.1, res=res, out_dtype=torch.float32, impl=impl)
+        ref = F.leaky_relu(_ref_conv(x, cw.w.float().reshape(3, 3, 320, 960).permute(2, 3, 0, 1).contiguous(),
+                                     b.to(cuda), 3, 1, x2), 0.1) + res.float()
+        _close(out, ref, 5e-3)
+    resf = res.float()
+    out = ops.igemm(x, cw, x2=x2, act=ops.ACT_SILU, res=resf)
+    ref = F.silu(_ref_conv(x, cw.w.float().reshape(3, 3, 320, 960).permute(2, 3, 0, 1).contiguous(), b.to(cuda), 3, 1, x2)) + resf
+    _close(out, ref)
+
+
+def test_channel_slice_views(cuda):
+    """inputs / outputs / residuals that are channel slices of wider buffers (zero-copy concat)."""
+    from onedc_b200 import ops
+    buf = _mk((1, 16, 16, 256), cuda, 1)
+    outbuf = torch.zeros((1, 16, 16, 512), device=cuda, dtype=torch.bfloat16)
+    wt = _mk((256, 128, 1, 1), "cpu", 2, scale=128 ** -0.5).float()
+    cw = ops.ConvW(wt, None, cuda)
+    ops.igemm(buf[..., 128:], cw, out=outbuf[..., 256:], res=buf)
+    ref = _ref_conv(buf[..., 128:], cw.w.float().reshape(1, 1, 256, 128).permute(2, 3, 0, 1).contiguous(), None, 1, 1) + buf.float()
+    _close(outbuf[..., 256:], ref)
+    assert outbuf[..., :256].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("mode", ["pair", "geglu"])
+def test_pair_epilogues(cuda, mode):
+    from onedc_b200 import ops
+    from onedc_b200.lib import EPI_GEGLU, EPI_PAIR_LRELU
+    c = 256
+    x = _mk((1, 20, 20, c), cuda, 1)
+    wt = _mk((4 * c, c), "cpu", 2, scale=c ** -0.5).float()
+    b = _mk((4 * c,), "cpu", 3).float()
+    wp, bp = ops.pair_permute(wt, b, 256)
+    cw = ops.ConvW(wp, bp, cuda, epi=EPI_PAIR_LRELU if mode == "pair" else EPI_GEGLU, bn=256)
+    y = F.linear(x.float(), wt.to(torch.bfloat16).float().to(cuda), b.to(cuda))
+    a, g = y.chunk(2, dim=-1)
+    ref = F.leaky_relu(a, 0.1) + F.leaky_relu(g, 0.01) if mode == "pair" else a * F.gelu(g)
+    for impl in (0, 1):
+        out = ops.igemm(x, cw, impl=impl)
+        assert out.shape[-1] == 2 * c
+        _close(out, ref)
+
+
+def test_pixel_shuffle_store(cuda):
+    from onedc_b200 import ops
+    from onedc_b200.lib import ST_PIXSHUF
+    cin, cout = 128, 256
+    x = _mk((2, 12, 12, cin), cuda, 1)
+    wt = _mk((4 * cout, cin), "cpu", 2, scale=cin ** -0.5).float()
+    b = _mk((4 * cout,), "cpu", 3).float()
+    cw = ops.ConvW(*ops.pixshuf_permute(wt, b), cuda)
+    y = F.linear(x.float(), wt.to(torch.bfloat16).float().to(cuda), b.to(cuda)).permute(0, 3, 1, 2)
+    ref = F.pixel_shuffle(F.leaky_relu(y, 0.01), 2).permute(0, 2, 3, 1)
+    for impl in (0, 1):
+        out = ops.igemm(x, cw, act=ops.ACT_LRELU, slope=0.01, store=ST_PIXSHUF, ps_c=cout, impl=impl)
+        _close(out, ref)
+
+
+def test_transposed_store_and_batched_b(cuda):
+    from onedc_b200 import ops
+    from onedc_b200.lib import ST_TRANSPOSED
+    b_, s, c = 3, 144, 768
+    x = _mk((b_, 1, s, c), cuda, 1)
+    wt = _mk((c, c), "cpu", 2, scale=c ** -0.5).float()
+    cw = ops.ConvW(wt, None, cuda)
+    vT = torch.zeros((b_, c, 152), device=cuda, dtype=torch.bfloat16)
+    ops.igemm(x, cw, store=ST_TRANSPOSED, out=vT)
+    ref = F.linear(x.float(), wt.to(torch.bfloat16).float().to(cuda))[:, 0].transpose(1, 2)
+    _close(vT[:, :, :s], ref)
+    assert vT[:, :, s:].abs().max().item() == 0
+    # batched B: scores[b] = q[b] k[b]^T
+    q, k = _mk((b_, s, c), cuda, 3, 0.2), _mk((b_, s, c), cuda, 4, 0.2)
+    sc = torch.zeros((b_, 1, s, 152), device=cuda, dtype=torch.float32)
+    ops.igemm(q[:, None], k, out=sc[..., :s], w_batched=True)
+    _close(sc[:, 0, :, :s], torch.bmm(q.float(), k.float().transpose(1, 2)), 2e-3)
+
+
+def test_large_layer_shapes(cuda):
+    """the biggest VAE layer shape (256 ch @ 768^2 is 38 GB of MACs; use a 192^2 crop of it) and N=128 tiles."""
+    from onedc_b200 import ops
+    for c, hw in ((256, 192), (128, 256)):
+        x = _mk((1, hw, hw, c), cuda, 1)
+        wt = _mk((c, c, 3, 3), "cpu", 2, scale=(9 * c) ** -0.5).float()
+        cw = ops.ConvW(wt, None, cuda)
+        out = ops.igemm(x, cw)
+        ref = _ref_conv(x, cw.w.float().reshape(3, 3, c, c).permute(2, 3, 0, 1).contiguous(), None, 3, 1)
+        _close(out, ref)
