@@ -338,7 +338,7 @@ class TimestepEmbedding(nn.Module):
 def sinusoidal_timestep(t, dim=320):
     """diffusers Timesteps(320, flip_sin_to_cos=True, downscale_freq_shift=0)."""
     half = dim // 2
-    e = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    e = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     a = t.float()[:, None] * e[None, :]
     return torch.cat([torch.cos(a), torch.sin(a)], dim=-1)
 

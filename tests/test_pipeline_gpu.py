@@ -70,7 +70,7 @@ def test_roundtrip_lossless_and_entropy_bit_exact(bundle):
         assert torch.equal(t["y_hat"], e["y_hat"]), f"step {k}: y_hat differs between encoder and decoder"
         # indices bit-exact vs the oracle formula on the SAME (product) scales
         ref_idx = E.build_indexes(E.combine_for_writing(t["scales"].permute(0, 3, 1, 2) * masks[k]))
-        assert torch.equal(t["idx"].view(-1).int(), ref_idx.view(-1)), f"step {k}: index kernel != oracle"
+        assert torch.equal(t["idx"].reshape(-1).int(), ref_idx.reshape(-1)), f"step {k}: index kernel != oracle"
         # oracle C rANS decodes the same symbols from the same bytes
         sym_o = orc.rans.decode(t["idx"].view(-1).numpy())
         assert np.array_equal(sym_o, t["sym"].view(-1).numpy()), f"step {k}: oracle rANS decode differs"
