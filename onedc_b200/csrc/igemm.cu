@@ -31,7 +31,8 @@ namespace onedc {
 constexpr int kMaxStages = 8;
 constexpr int kABytes = 128 * 128;       // 128 rows x 64 bf16
 constexpr int kSmemBudget = 200 * 1024;  // operand ring
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;            // two warps per TMEM lane quarter, splitting the columns
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 
 struct IgemmParams {
   // geometry
@@ -188,6 +189,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   __shared__ __align__(8) uint64_t tmem_full[2];
   __shared__ __align__(8) uint64_t tmem_empty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float bias_s[2][256];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -200,7 +202,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);   // one arrive per epilogue warp
+      mbar_init(&tmem_empty[a], kEpiWarps);   // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -283,22 +285,137 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       }
     }
   } else {
-    // ===================== epilogue warps (TMEM lane quarter = warp % 4) =====================
+    // ===================== epilogue warps =====================
+    // warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps of a quarter interleave 32-column chunks.
     const int q = warp & 3;
+    const int member = (warp - 2) >> 2;
+    const int etid = threadIdx.x - 64;                 // 0..255 among epilogue threads
     const int row = q * 32 + lane;
     const int ry = row / p.TW, rx = row - ry * p.TW;
+    const bool pair = p.epi_mode != EPI_PLAIN;
+    const int half = p.BN >> 1;
+    const int out_cols_tile = pair ? half : p.BN;      // output columns produced per tile
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
       const int acc = it & 1;
       TileCoord t = decode_tile(p, tile);
       const int y = t.y0 + ry, x = t.x0 + rx;
       const bool valid = (ry < p.TH) && (y < p.H) && (x < p.W);
+      const int n0 = t.n_tile * p.BN;
+      // stage this tile's bias slice (GEMM column order) in shared memory
+      if (etid < p.BN) bias_s[acc][etid] = (p.bias != nullptr && n0 + etid < p.cout) ? __ldg(p.bias + n0 + etid) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-      const int n0 = t.n_tile * p.BN;
-      if (p.epi_mode == EPI_PLAIN) {
-        for (int c = 0; c < p.BN; c += 16) {
+      const int o0 = t.n_tile * out_cols_tile;         // first output column of this tile
+      const bool fast = p.vec_ok && (o0 + out_cols_tile <= p.ncols_out) && (out_cols_tile % 32 == 0) &&
+                        (p.store_mode == ST_NORMAL || (p.store_mode == ST_PIXSHUF && p.ps_c % 32 == 0));
+      if (fast) {
+        const long long pix = ((long long)t.img * p.H + y) * p.W + x;
+        for (int c = member * 32; c < out_cols_tile; c += 64) {
+          float v[32];
+          {
+            uint32_t r[32];
+            tmem_ld32(taddr + c, r);
+            if (pair) {
+              uint32_t r2[32];
+              tmem_ld32(taddr + half + c, r2);
+              tmem_ld_wait();
+              const float4* ba = reinterpret_cast<const float4*>(&bias_s[acc][c]);
+              const float4* bb = reinterpret_cast<const float4*>(&bias_s[acc][half + c]);
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                const float4 a4 = ba[i], b4 = bb[i];
+                const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                  const float va = __uint_as_float(r[4 * i + j]) + av[j];
+                  const float vb = __uint_as_float(r2[4 * i + j]) + bv[j];
+                  if (p.epi_mode == EPI_PAIR_LRELU)
+                    v[4 * i + j] = (va > 0.f ? va : 0.1f * va) + (vb > 0.f ? vb : 0.01f * vb);
+                  else
+                    v[4 * i + j] = va * (0.5f * vb * (1.f + erff(vb * 0.70710678118654752f)));
+                }
+              }
+            } else {
+              tmem_ld_wait();
+              const float4* ba = reinterpret_cast<const float4*>(&bias_s[acc][c]);
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                const float4 a4 = ba[i];
+                v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + a4.x;
+                v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + a4.y;
+                v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + a4.z;
+                v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + a4.w;
+              }
+              if (p.act == ACT_LRELU) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) v[i] = v[i] > 0.f ? v[i] : v[i] * p.slope;
+              } else if (p.act == ACT_SILU) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) v[i] = __fdividef(v[i], 1.f + __expf(-v[i]));
+              } else if (p.act == ACT_GELU) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
+              }
+            }
+          }
+          if (valid) {
+            const int ocol = o0 + c;
+            if (p.res != nullptr) {
+              if (p.res_dtype == DT_BF16) {
+                const uint4* r4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) +
+                                                                 pix * p.res_ld + ocol);
+                uint4 qv[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) qv[i] = __ldg(r4 + i);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                  v[8 * i + 0] += bf16lo(qv[i].x); v[8 * i + 1] += bf16hi(qv[i].x);
+                  v[8 * i + 2] += bf16lo(qv[i].y); v[8 * i + 3] += bf16hi(qv[i].y);
+                  v[8 * i + 4] += bf16lo(qv[i].z); v[8 * i + 5] += bf16hi(qv[i].z);
+                  v[8 * i + 6] += bf16lo(qv[i].w); v[8 * i + 7] += bf16hi(qv[i].w);
+                }
+              } else {
+                const float4* r4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) +
+                                                                   pix * p.res_ld + ocol);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                  const float4 f = __ldg(r4 + i);
+                  v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+                }
+              }
+            }
+            long long opix = pix;
+            int oc = ocol;
+            if (p.store_mode == ST_PIXSHUF) {
+              const int qd = ocol / p.ps_c;
+              oc = ocol - qd * p.ps_c;
+              opix = ((long long)t.img * (2 * p.H) + (2 * y + (qd >> 1))) * (2 * p.W) + (2 * x + (qd & 1));
+            }
+            const long long o = opix * p.out_ld + p.out_col_off + oc;
+            if (p.out_dtype == DT_BF16) {
+              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                uint4 w4;
+                w4.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+                w4.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+                w4.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+                w4.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+                dst[i] = w4;
+              }
+            } else {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
+#pragma unroll
+              for (int i = 0; i < 8; i++) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+          }
+        }
+      } else if (!pair) {
+        // generic path (partial N tiles, transposed / unaligned stores): 16 columns at a time
+        for (int c = member * 16; c < p.BN; c += 32) {
           uint32_t r[16];
           tmem_ld16(taddr + c, r);
           tmem_ld_wait();
@@ -310,8 +427,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           }
         }
       } else {
-        const int half = p.BN >> 1;
-        for (int c = 0; c < half; c += 16) {
+        for (int c = member * 16; c < half; c += 32) {
           uint32_t r0[16], r1[16];
           tmem_ld16(taddr + c, r0);
           tmem_ld16(taddr + half + c, r1);
@@ -470,10 +586,12 @@ static void pick_tile(int H, int W, int* th, int* tw) {
     *tw = 128;
     return;
   }
+  // fewest tiles wins; ties go to the most square box (best halo reuse in L2 for 3x3 taps)
+  const int cand[7] = {16, 8, 32, 4, 64, 2, 128};
   long long best = -1;
-  for (int t = 128; t >= 2; t >>= 1) {  // tw candidates 128..2
-    int h = 128 / t;
-    long long tiles = (long long)((H + h - 1) / h) * ((W + t - 1) / t);
+  for (int i = 0; i < 7; i++) {
+    const int t = cand[i], h = 128 / t;
+    const long long tiles = (long long)((H + h - 1) / h) * ((W + t - 1) / t);
     if (best < 0 || tiles < best) {
       best = tiles;
       *th = h;

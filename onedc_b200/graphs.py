@@ -1,0 +1,147 @@
+"""CUDA-graph execution of the decode path.
+
+The eager path issues ~870 kernel launches per 768x768 image from Python; on a B200 that is launch-bound.  The decode
+has a fixed structure per (batch, H, W), broken only by the four host rANS calls, so it is captured once into five
+graphs (one graph for the device-resident leg) and replayed:
+
+    G0 : FSQ codes -> hyper-synthesis -> prior fusion -> reduction -> index kernel(step 0) -> D2H indices
+    Gk : H2D symbols(k-1) -> dequant(k-1) -> adaptor_k + prior net -> index kernel(k) -> D2H indices      k = 1..3
+    G4 : H2D symbols(3) -> dequant(3) -> semantic adaptor -> g_s -> UNet -> x0 -> VAE -> D2H image
+
+Host<->device copies use fixed pinned buffers and are graph nodes; TMA descriptors are encoded at capture time against
+the (static) addresses of the graph's private memory pool.
+"""
+import numpy as np
+import torch
+
+from . import bitstream, ops
+from .entropy_models import StreamDecoder
+
+
+class GraphedDecoder:
+    def __init__(self, model, batch, height, width):
+        assert height % 64 == 0 and width % 64 == 0, "graphs are keyed by the padded size"
+        self.model, self.codec = model, model.codec_model
+        self.B, self.H, self.W = batch, height, width
+        dev = model.device
+        self.dev = dev
+        self.hz, self.wz = height // 64, width // 64
+        self.h16, self.w16 = height // 16, width // 16
+        self.nsym = 32 * self.h16 * self.w16
+        B = batch
+        self.z_host = torch.zeros((B, self.hz, self.wz), dtype=torch.int32, pin_memory=True)
+        self.z_dev = torch.zeros((B, self.hz, self.wz), dtype=torch.int32, device=dev)
+        self.idx_host = torch.zeros((B, self.nsym), dtype=torch.int16, pin_memory=True)
+        self.sym_host = torch.zeros((B, self.nsym), dtype=torch.int16, pin_memory=True)
+        self.idx_dev = torch.zeros((B, 32, self.h16, self.w16), dtype=torch.int16, device=dev)
+        self.sym_dev = torch.zeros((B, 32, self.h16, self.w16), dtype=torch.int16, device=dev)
+        self.img_host = torch.zeros((B, 3, height, width), dtype=torch.float32, pin_memory=True)
+        self.syms_res = [torch.zeros((B, 32, self.h16, self.w16), dtype=torch.int16, device=dev) for _ in range(4)]
+        self.graphs = None
+        self.g_res = None
+        self.img_dev = None
+        self._keep = []
+
+    # ---------------------------------------------------------------------------------------------
+    def _seg0(self):
+        c = self.codec
+        self.common, self.z_sem = c.hyper(self.z_dev)
+        self.params = c.prior.init_params(self.common)
+        self.sm = [self.common, None, None, None]
+        ops.scale_to_index(self.common[..., :128], c._lut(), 0, self.idx_dev)
+        self.idx_host.copy_(self.idx_dev.view(self.B, self.nsym), non_blocking=True)
+
+    def _segk(self, k):
+        c = self.codec
+        self.sym_dev.view(self.B, self.nsym).copy_(self.sym_host, non_blocking=True)
+        ops.dequant_accum(self.sym_dev, self.sm[k - 1][..., 128:], self.params[..., :128], k - 1)
+        self.sm[k] = c.prior.step(k, self.params)
+        ops.scale_to_index(self.sm[k][..., :128], c._lut(), k, self.idx_dev)
+        self.idx_host.copy_(self.idx_dev.view(self.B, self.nsym), non_blocking=True)
+
+    def _seg4(self):
+        c = self.codec
+        self.sym_dev.view(self.B, self.nsym).copy_(self.sym_host, non_blocking=True)
+        ops.dequant_accum(self.sym_dev, self.sm[3][..., 128:], self.params[..., :128], 3)
+        y_sem = c.semantic_adaptor(self.z_sem)
+        x_hat = c.dec(self.params[..., :128], y_sem)
+        self.img_dev = self.model.generate(x_hat, y_sem)
+        self.img_host.copy_(self.img_dev, non_blocking=True)
+
+    def _segments(self):
+        return [self._seg0, lambda: self._segk(1), lambda: self._segk(2), lambda: self._segk(3), self._seg4]
+
+    def capture(self):
+        """Warm up eagerly once (function attributes, allocator), then capture the five segments into one pool."""
+        if self.graphs is not None:
+            return
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s), torch.no_grad():
+            for seg in self._segments():
+                seg()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        from . import lib
+        pool = torch.cuda.graph_pool_handle()
+        self.graphs = []
+        n0 = lib.launch_count()
+        with torch.no_grad():
+            for seg in self._segments():
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    seg()
+                self.graphs.append(g)
+        self.launches = lib.launch_count() - n0
+        torch.cuda.synchronize()
+
+    def capture_resident(self):
+        if self.g_res is not None:
+            return
+        from . import lib
+        with torch.no_grad():
+            self.model.decode_resident(self.z_dev, self.syms_res)
+            torch.cuda.synchronize()
+            n0 = lib.launch_count()
+            self.g_res = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_res):
+                self.img_res = self.model.decode_resident(self.z_dev, self.syms_res)
+            self.launches_res = lib.launch_count() - n0      # kernels of this library inside one replay
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------------------------------------
+    def decode(self, streams):
+        """streams: B reference-format containers of this padded size -> pinned host images [B,3,H,W] fp32
+        (padded; crop with the returned headers).  Host rANS runs between graph replays."""
+        assert len(streams) == self.B
+        self.capture()
+        c = self.codec
+        hdrs = [bitstream.decode_i(s, c.index_unit_length, c.ds) for s in streams]
+        for i, d in enumerate(hdrs):
+            assert (d["pad_height"], d["pad_width"]) == (self.H, self.W)
+            self.z_host[i] = torch.from_numpy(bitstream.unpack_indices(d["bit_stream_z"], self.hz * self.wz,
+                                                                       c.index_unit_length).reshape(self.hz, self.wz))
+        decoders = [StreamDecoder(c.entropy_coder, d["bit_stream_y"], c.gaussian_encoder.cdf_group_index) for d in hdrs]
+        stream = torch.cuda.current_stream()
+        self.z_dev.copy_(self.z_host, non_blocking=True)
+        ip, sp, n = self.idx_host.data_ptr(), self.sym_host.data_ptr(), self.nsym
+        for k in range(4):
+            self.graphs[k].replay()
+            stream.synchronize()
+            if self.B == 1:
+                decoders[0].decode_into(ip, n, sp)
+            else:
+                list(c._pool.map(lambda i: decoders[i].decode_into(ip + 2 * i * n, n, sp + 2 * i * n), range(self.B)))
+        self.graphs[4].replay()
+        stream.synchronize()
+        return self.img_host, hdrs
+
+    def set_resident_inputs(self, z_idx, syms):
+        self.z_dev.copy_(z_idx)
+        for a, b in zip(self.syms_res, syms):
+            a.copy_(b)
+
+    def run_resident(self):
+        self.capture_resident()
+        self.g_res.replay()
+        return self.img_res

@@ -147,3 +147,15 @@ def test_batch_decode_matches_single(bundle):
     b = model.decode(stream=s2)
     both = model.decode_batch([bundle["stream"], s2])
     assert _psnr01(both[0].cpu(), a.cpu()) > 60 and _psnr01(both[1].cpu(), b.cpu()) > 60
+
+
+def test_graph_replay_matches_eager(bundle):
+    """CUDA-graph replay (the default decode route) must be bit-identical to eager launches, run after run."""
+    model = bundle["model"]
+    eager = model.decode(stream=bundle["stream"], stages={})
+    g1 = model.decode(stream=bundle["stream"])
+    g2 = model.decode(stream=bundle["stream"])
+    assert torch.equal(g1, g2), "graph replays differ run to run"
+    assert torch.equal(eager, g1), "graph replay differs from eager"
+    host = model.last_host_images
+    assert torch.equal(host[:, :, :H, :W], g1.cpu())
