@@ -96,6 +96,12 @@ typedef struct {
   int32_t ps_c;
   int32_t bn;           /* N tile, multiple of 16 (32 for pair modes), <= 256; 0 = auto */
   int32_t impl;         /* 0 = tcgen05 kernel, 1 = SIMT checking kernel (debug only) */
+  /* optional split-K scratch (layers with too few tiles to fill the GPU): fp32 workspace and per-tile int32
+   * arrival counters that are zero on entry and zero again on exit; NULL disables split-K */
+  void* splitk_ws;
+  int64_t splitk_ws_floats;
+  void* splitk_counters;
+  int32_t splitk_max_tiles; /* number of counters */
 } onedc_igemm_desc;
 
 int onedc_igemm(const onedc_igemm_desc* d, void* stream);
@@ -107,12 +113,13 @@ int onedc_attention(const void* q, int64_t q_ld, const void* k, const void* v, i
                     float scale, int32_t impl, void* stream);
 
 /* ---- normalisation / elementwise --------------------------------------------------------- */
-/* GroupNorm over the channel concatenation of up to two NHWC sources. partial: fp32 workspace of
- * onedc_groupnorm_ws_floats() floats; stats: fp32 [n_img][groups][2] (mean, rstd). */
+/* GroupNorm over the channel concatenation of up to two NHWC sources. acc: fp64 scratch [n_img][groups][2]
+ * (onedc_groupnorm_ws_floats() floats) and counters: n_img uint32 -- both zero on entry and zero again on exit
+ * (the last block of an image finalises and cleans up); stats: fp32 [n_img][groups][2] (mean, rstd). */
 int64_t onedc_groupnorm_ws_floats(int32_t n_img, int64_t hw, int32_t c_total);
 int onedc_groupnorm_stats(const void* x0, int32_t c0, int64_t ld0, const void* x1, int32_t c1, int64_t ld1,
-                          int32_t in_dtype, int32_t n_img, int64_t hw, int32_t groups, float eps, float* partial,
-                          float* stats, void* stream);
+                          int32_t in_dtype, int32_t n_img, int64_t hw, int32_t groups, float eps, double* acc,
+                          float* stats, uint32_t* counters, void* stream);
 int onedc_groupnorm_apply(const void* x0, int32_t c0, int64_t ld0, const void* x1, int32_t c1, int64_t ld1,
                           int32_t in_dtype, int32_t n_img, int64_t hw, int32_t groups, const float* stats,
                           const float* gamma, const float* beta, int32_t silu, void* out, int64_t out_ld,

@@ -56,6 +56,11 @@ struct IgemmParams {
   int out_col_off, store_mode, ps_c;
   int ncols_out;          // cout (plain) or cout/2 (pair modes)
   int vec_ok;
+  // split-K (small-M layers): fp32 partial tiles + per-tile arrival counters
+  int splits;
+  float* ws;
+  int* counters;
+  int counters_half;
   // raw views for the SIMT checker
   const __nv_bfloat16* a_ptr[2];
   int a_c[2];
@@ -180,6 +185,113 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile)
   return t;
 }
 
+// Finishes 32 output columns of one pixel: v[] already holds accumulator (+ nothing else) values.
+//   a[32]: accumulators of GEMM columns (n0 + c ..), b[32]: partner columns (pair modes only)
+//   bias_a / bias_b: shared-memory bias slices aligned with a / b
+template <bool PAIR>
+__device__ __forceinline__ void epi_finish32(const IgemmParams& p, float* a, const float* b, const float* bias_a,
+                                             const float* bias_b, bool valid, int img, int y, int x, long long pix,
+                                             int ocol) {
+  float* v = a;
+  if (!PAIR) {
+    const float4* ba = reinterpret_cast<const float4*>(bias_a);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const float4 a4 = ba[i];
+      v[4 * i + 0] += a4.x; v[4 * i + 1] += a4.y; v[4 * i + 2] += a4.z; v[4 * i + 3] += a4.w;
+    }
+    if (p.act == ACT_LRELU) {
+#pragma unroll
+      for (int i = 0; i < 32; i++) v[i] = v[i] > 0.f ? v[i] : v[i] * p.slope;
+    } else if (p.act == ACT_SILU) {
+#pragma unroll
+      for (int i = 0; i < 32; i++) v[i] = __fdividef(v[i], 1.f + __expf(-v[i]));
+    } else if (p.act == ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 32; i++) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
+    }
+  } else {
+    const float4* ba = reinterpret_cast<const float4*>(bias_a);
+    const float4* bb = reinterpret_cast<const float4*>(bias_b);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const float4 a4 = ba[i], b4 = bb[i];
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const float va = a[4 * i + j] + av[j];
+        const float vb = b[4 * i + j] + bv[j];
+        if (p.epi_mode == EPI_PAIR_LRELU)
+          v[4 * i + j] = (va > 0.f ? va : 0.1f * va) + (vb > 0.f ? vb : 0.01f * vb);
+        else
+          v[4 * i + j] = va * (0.5f * vb * (1.f + erff(vb * 0.70710678118654752f)));
+      }
+    }
+  }
+  if (!valid) return;
+  if (p.res != nullptr) {
+    if (p.res_dtype == DT_BF16) {
+      const uint4* r4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.res_ld + ocol);
+      uint4 qv[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) qv[i] = __ldg(r4 + i);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        v[8 * i + 0] += bf16lo(qv[i].x); v[8 * i + 1] += bf16hi(qv[i].x);
+        v[8 * i + 2] += bf16lo(qv[i].y); v[8 * i + 3] += bf16hi(qv[i].y);
+        v[8 * i + 4] += bf16lo(qv[i].z); v[8 * i + 5] += bf16hi(qv[i].z);
+        v[8 * i + 6] += bf16lo(qv[i].w); v[8 * i + 7] += bf16hi(qv[i].w);
+      }
+    } else {
+      const float4* r4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) + pix * p.res_ld + ocol);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float4 f = __ldg(r4 + i);
+        v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
+      }
+    }
+  }
+  long long opix = pix;
+  int oc = ocol;
+  if (p.store_mode == ST_PIXSHUF) {
+    const int qd = ocol / p.ps_c;
+    oc = ocol - qd * p.ps_c;
+    opix = ((long long)img * (2 * p.H) + (2 * y + (qd >> 1))) * (2 * p.W) + (2 * x + (qd & 1));
+  }
+  const long long o = opix * p.out_ld + p.out_col_off + oc;
+  if (p.out_dtype == DT_BF16) {
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint4 w4;
+      w4.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+      w4.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+      w4.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+      w4.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+      dst[i] = w4;
+    }
+  } else {
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
+#pragma unroll
+    for (int i = 0; i < 8; i++) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  }
+}
+
+// k-iteration index -> (tap, source, 64-channel chunk)
+struct KIter {
+  int tap, src, kc;
+};
+__device__ __forceinline__ KIter decode_kiter(const IgemmParams& p, int ki) {
+  const int per_tap = p.kchunks[0] + p.kchunks[1];
+  KIter k;
+  k.tap = ki / per_tap;
+  const int r = ki - k.tap * per_tap;
+  k.src = r >= p.kchunks[0] ? 1 : 0;
+  k.kc = k.src ? r - p.kchunks[0] : r;
+  return k;
+}
+
+template <bool SPLITK>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ IgemmParams p) {
@@ -189,6 +301,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   __shared__ __align__(8) uint64_t tmem_full[2];
   __shared__ __align__(8) uint64_t tmem_empty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ int last_flag;
   __shared__ __align__(16) float bias_s[2][256];
 
   const int warp = threadIdx.x >> 5;
@@ -217,7 +330,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  // work item = (tile, k-split); splits of one tile are adjacent items, i.e. run on different CTAs
+  const int nsplit = SPLITK ? p.splits : 1;
+  const int total_items = p.m_tiles * p.n_tiles * nsplit;
+  const int kiters = p.taps * (p.kchunks[0] + p.kchunks[1]);
   const uint32_t a_bytes = (uint32_t)(p.TH * p.TW) * 128u;
   const uint32_t b_bytes = (uint32_t)p.BN * 128u;
 
@@ -226,27 +342,25 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int tile = item / nsplit, split = item - tile * nsplit;
         TileCoord t = decode_tile(p, tile);
         const int n0 = t.n_tile * p.BN;
-        for (int tap = 0; tap < p.taps; tap++) {
-          const int bz = p.w_batched ? t.img : tap;
-          for (int src = 0; src < 2; src++) {
-            const CUtensorMap* ma = src ? &map_a1 : &map_a0;
-            const int kb = src ? p.c1_off : 0;
-            for (int kc = 0; kc < p.kchunks[src]; kc++) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-              uint8_t* sb = sa + kABytes;
-              mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-              tma_load_5d(sa, ma, &full_bar[stage], p.tap_dc[tap] + kc * 64, t.x0 + p.tap_dx[tap], p.tap_dp[tap],
-                          t.y0 + p.tap_dy[tap], t.img);
-              tma_load_3d(sb, &map_b, &full_bar[stage], kb + kc * 64, n0, bz);
-              if (++stage == p.stages) {
-                stage = 0;
-                phase ^= 1;
-              }
-            }
+        const int k0 = (int)((long long)kiters * split / nsplit), k1 = (int)((long long)kiters * (split + 1) / nsplit);
+        for (int ki = k0; ki < k1; ki++) {
+          const KIter k = decode_kiter(p, ki);
+          const CUtensorMap* ma = k.src ? &map_a1 : &map_a0;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+          tma_load_5d(sa, ma, &full_bar[stage], p.tap_dc[k.tap] + k.kc * 64, t.x0 + p.tap_dx[k.tap], p.tap_dp[k.tap],
+                      t.y0 + p.tap_dy[k.tap], t.img);
+          tma_load_3d(sb, &map_b, &full_bar[stage], (k.src ? p.c1_off : 0) + k.kc * 64, n0,
+                      p.w_batched ? t.img : k.tap);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
           }
         }
       }
@@ -255,16 +369,17 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
-      const int kiters = p.taps * (p.kchunks[0] + p.kchunks[1]);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, it++) {
+        const int split = item % nsplit;
+        const int k0 = (int)((long long)kiters * split / nsplit), k1 = (int)((long long)kiters * (split + 1) / nsplit);
         const int acc = it & 1;
         mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int ki = 0; ki < kiters; ki++) {
+        for (int ki = k0; ki < k1; ki++) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
@@ -273,7 +388,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
 #pragma unroll
           for (int k = 0; k < 4; k++) {
             // +32 bytes (16 bf16) along K inside the 128B swizzle atom == +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (ki | k) != 0);
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, ((ki - k0) | k) != 0);
           }
           umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs have read it
           if (++stage == p.stages) {
@@ -296,7 +411,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     const int half = p.BN >> 1;
     const int out_cols_tile = pair ? half : p.BN;      // output columns produced per tile
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it++) {
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, it++) {
+      const int tile = item / nsplit, split = item - tile * nsplit;
       const int acc = it & 1;
       TileCoord t = decode_tile(p, tile);
       const int y = t.y0 + ry, x = t.x0 + rx;
@@ -309,12 +425,88 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
       const int o0 = t.n_tile * out_cols_tile;         // first output column of this tile
+      const long long pix = ((long long)t.img * p.H + y) * p.W + x;
       const bool fast = p.vec_ok && (o0 + out_cols_tile <= p.ncols_out) && (out_cols_tile % 32 == 0) &&
                         (p.store_mode == ST_NORMAL || (p.store_mode == ST_PIXSHUF && p.ps_c % 32 == 0));
+      if (SPLITK) {
+        // ---- split-K (one work item per CTA, all co-resident): park the raw fp32 accumulators, wait until all
+        //      splits of this tile have done so, then reduce a row slice of the tile in split order (deterministic)
+        //      and run the real epilogue on it.  The host only enables this on the vector-store fast layout.
+        float* wrow = p.ws + ((size_t)item * 128 + row) * p.BN;
+        for (int c = member * 32; c < p.BN; c += 64) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c, r);
+          tmem_ld_wait();
+          float4* d4 = reinterpret_cast<float4*>(wrow + c);
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+            __stcg(d4 + i, make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                       __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);  // TMEM buffer is free again
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (etid == 0) {
+          atomicAdd(p.counters + tile, 1);
+          volatile int* cnt = p.counters + tile;
+          while (*cnt < p.splits) __nanosleep(40);
+          __threadfence();
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int r0 = 128 * split / p.splits, r1 = 128 * (split + 1) / p.splits;
+        const int nch = out_cols_tile >> 5;
+        const int tasks = (r1 - r0) * nch;
+        const size_t sstride = (size_t)128 * p.BN;
+        for (int task = etid; task < tasks; task += 256) {
+          const int rr = r0 + task / nch, c = (task % nch) << 5;
+          const int yy = t.y0 + rr / p.TW, xx = t.x0 + rr % p.TW;
+          const bool vld = (rr < p.TH * p.TW) && (yy < p.H) && (xx < p.W);
+          const float* wbase = p.ws + ((size_t)tile * p.splits * 128 + rr) * p.BN;
+          float a[32], b[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) a[i] = 0.f;
+          if (pair) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) b[i] = 0.f;
+          }
+          for (int s2 = 0; s2 < p.splits; s2++) {
+            const float4* s4 = reinterpret_cast<const float4*>(wbase + s2 * sstride + c);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const float4 f = __ldcg(s4 + i);
+              a[4 * i] += f.x; a[4 * i + 1] += f.y; a[4 * i + 2] += f.z; a[4 * i + 3] += f.w;
+            }
+            if (pair) {
+              const float4* t4 = reinterpret_cast<const float4*>(wbase + s2 * sstride + half + c);
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                const float4 f = __ldcg(t4 + i);
+                b[4 * i] += f.x; b[4 * i + 1] += f.y; b[4 * i + 2] += f.z; b[4 * i + 3] += f.w;
+              }
+            }
+          }
+          const long long pix2 = ((long long)t.img * p.H + yy) * p.W + xx;
+          if (pair)
+            epi_finish32<true>(p, a, b, &bias_s[acc][c], &bias_s[acc][half + c], vld, t.img, yy, xx, pix2, o0 + c);
+          else
+            epi_finish32<false>(p, a, a, &bias_s[acc][c], &bias_s[acc][c], vld, t.img, yy, xx, pix2, o0 + c);
+        }
+        // last CTA to finish re-arms the counters (nobody can still be spinning: all have passed the wait)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (etid == 0) {
+          const int old = atomicAdd(p.counters + p.counters_half + tile, 1);
+          if (old == p.splits - 1) {
+            p.counters[tile] = 0;
+            p.counters[p.counters_half + tile] = 0;
+          }
+        }
+        continue;
+      }
       if (fast) {
-        const long long pix = ((long long)t.img * p.H + y) * p.W + x;
         for (int c = member * 32; c < out_cols_tile; c += 64) {
-          float v[32];
+          float a[32], b[32];
           {
             uint32_t r[32];
             tmem_ld32(taddr + c, r);
@@ -322,96 +514,18 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
               uint32_t r2[32];
               tmem_ld32(taddr + half + c, r2);
               tmem_ld_wait();
-              const float4* ba = reinterpret_cast<const float4*>(&bias_s[acc][c]);
-              const float4* bb = reinterpret_cast<const float4*>(&bias_s[acc][half + c]);
 #pragma unroll
-              for (int i = 0; i < 8; i++) {
-                const float4 a4 = ba[i], b4 = bb[i];
-                const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                  const float va = __uint_as_float(r[4 * i + j]) + av[j];
-                  const float vb = __uint_as_float(r2[4 * i + j]) + bv[j];
-                  if (p.epi_mode == EPI_PAIR_LRELU)
-                    v[4 * i + j] = (va > 0.f ? va : 0.1f * va) + (vb > 0.f ? vb : 0.01f * vb);
-                  else
-                    v[4 * i + j] = va * (0.5f * vb * (1.f + erff(vb * 0.70710678118654752f)));
-                }
-              }
+              for (int i = 0; i < 32; i++) b[i] = __uint_as_float(r2[i]);
             } else {
               tmem_ld_wait();
-              const float4* ba = reinterpret_cast<const float4*>(&bias_s[acc][c]);
-#pragma unroll
-              for (int i = 0; i < 8; i++) {
-                const float4 a4 = ba[i];
-                v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + a4.x;
-                v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + a4.y;
-                v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + a4.z;
-                v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + a4.w;
-              }
-              if (p.act == ACT_LRELU) {
-#pragma unroll
-                for (int i = 0; i < 32; i++) v[i] = v[i] > 0.f ? v[i] : v[i] * p.slope;
-              } else if (p.act == ACT_SILU) {
-#pragma unroll
-                for (int i = 0; i < 32; i++) v[i] = __fdividef(v[i], 1.f + __expf(-v[i]));
-              } else if (p.act == ACT_GELU) {
-#pragma unroll
-                for (int i = 0; i < 32; i++) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
-              }
             }
+#pragma unroll
+            for (int i = 0; i < 32; i++) a[i] = __uint_as_float(r[i]);
           }
-          if (valid) {
-            const int ocol = o0 + c;
-            if (p.res != nullptr) {
-              if (p.res_dtype == DT_BF16) {
-                const uint4* r4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) +
-                                                                 pix * p.res_ld + ocol);
-                uint4 qv[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) qv[i] = __ldg(r4 + i);
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                  v[8 * i + 0] += bf16lo(qv[i].x); v[8 * i + 1] += bf16hi(qv[i].x);
-                  v[8 * i + 2] += bf16lo(qv[i].y); v[8 * i + 3] += bf16hi(qv[i].y);
-                  v[8 * i + 4] += bf16lo(qv[i].z); v[8 * i + 5] += bf16hi(qv[i].z);
-                  v[8 * i + 6] += bf16lo(qv[i].w); v[8 * i + 7] += bf16hi(qv[i].w);
-                }
-              } else {
-                const float4* r4 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.res) +
-                                                                   pix * p.res_ld + ocol);
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                  const float4 f = __ldg(r4 + i);
-                  v[4 * i] += f.x; v[4 * i + 1] += f.y; v[4 * i + 2] += f.z; v[4 * i + 3] += f.w;
-                }
-              }
-            }
-            long long opix = pix;
-            int oc = ocol;
-            if (p.store_mode == ST_PIXSHUF) {
-              const int qd = ocol / p.ps_c;
-              oc = ocol - qd * p.ps_c;
-              opix = ((long long)t.img * (2 * p.H) + (2 * y + (qd >> 1))) * (2 * p.W) + (2 * x + (qd & 1));
-            }
-            const long long o = opix * p.out_ld + p.out_col_off + oc;
-            if (p.out_dtype == DT_BF16) {
-              uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
-#pragma unroll
-              for (int i = 0; i < 4; i++) {
-                uint4 w4;
-                w4.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-                w4.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-                w4.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-                w4.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-                dst[i] = w4;
-              }
-            } else {
-              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
-#pragma unroll
-              for (int i = 0; i < 8; i++) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
-          }
+          if (pair)
+            epi_finish32<true>(p, a, b, &bias_s[acc][c], &bias_s[acc][half + c], valid, t.img, y, x, pix, o0 + c);
+          else
+            epi_finish32<false>(p, a, a, &bias_s[acc][c], &bias_s[acc][c], valid, t.img, y, x, pix, o0 + c);
         }
       } else if (!pair) {
         // generic path (partial N tiles, transposed / unaligned stores): 16 columns at a time
@@ -696,6 +810,28 @@ static int igemm_launch(const onedc_igemm_desc* d, cudaStream_t stream) {
   p.w_row = d->w_row_stride;
   p.w_z = d->w_z_stride;
 
+  // ---- split-K for layers with too few tiles to fill the GPU (UNet 24x24 / 12x12 levels): only on the
+  //      vector-store fast path, with caller-provided scratch; each split keeps >= 8 k-iterations
+  p.splits = 1;
+  p.ws = reinterpret_cast<float*>(d->splitk_ws);
+  p.counters = reinterpret_cast<int*>(d->splitk_counters);
+  p.counters_half = d->splitk_max_tiles / 2;
+  {
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int kiters = p.taps * (p.kchunks[0] + p.kchunks[1]);
+    const int octile = pair ? p.BN / 2 : p.BN;
+    const bool fast_all = p.vec_ok && (d->cout % p.BN == 0) && (octile % 32 == 0) &&
+                          (d->store_mode == ST_NORMAL || (d->store_mode == ST_PIXSHUF && d->ps_c % 32 == 0));
+    if (d->impl == 0 && p.ws != nullptr && p.counters != nullptr && fast_all && tiles * 2 <= sm_count() &&
+        kiters >= 16 && tiles <= d->splitk_max_tiles / 2) {
+      int s = sm_count() / tiles;
+      if (s > kiters / 8) s = kiters / 8;
+      if (s > 16) s = 16;
+      while (s > 1 && (long long)tiles * s * 128 * p.BN > d->splitk_ws_floats) s--;
+      if (s >= 4) p.splits = s;
+    }
+  }
+
   if (d->impl == 1) {
     long long total = (long long)p.n_img * p.H * p.W * ((p.ncols_out + 15) / 16);
     int blocks = (int)((total + 127) / 128);
@@ -753,16 +889,21 @@ static int igemm_launch(const onedc_igemm_desc* d, cudaStream_t stream) {
     int rc = make_tensor_map(&mb, d->w_ptr, 3, dims, str, box);
     if (rc) return rc;
   }
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
   int grid = total_tiles < sm_count() ? total_tiles : sm_count();
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    ONEDC_CUDA(cudaFuncSetAttribute(igemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ONEDC_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBudget + 1024));
+    ONEDC_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSmemBudget + 1024));
     attr_set = true;
   }
-  igemm_tc_kernel<<<grid, kThreads, smem, stream>>>(ma[0], ma[1], mb, p);
+  if (p.splits > 1)
+    igemm_tc_kernel<true><<<grid, kThreads, smem, stream>>>(ma[0], ma[1], mb, p);
+  else
+    igemm_tc_kernel<false><<<grid, kThreads, smem, stream>>>(ma[0], ma[1], mb, p);
   count_launch();
   ONEDC_CUDA(cudaGetLastError());
   return 0;

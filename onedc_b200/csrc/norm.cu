@@ -6,7 +6,14 @@
 
 namespace onedc {
 
-__host__ __device__ inline int gn_chunk_pixels(long long hw) { return hw <= 1024 ? 16 : (hw <= 65536 ? 64 : 256); }
+// pixels per block of the statistics pass: ~4 blocks per SM on big tensors, >= 16 pixels on small ones
+__host__ __device__ inline int gn_chunk_pixels(long long hw, int slabs) {
+  long long target = 592 / (slabs > 0 ? slabs : 1);
+  if (target < 1) target = 1;
+  long long p = (hw + target - 1) / target;
+  p = (p + 15) / 16 * 16;
+  return (int)(p < 16 ? 16 : p);
+}
 
 __device__ __forceinline__ void load8(const void* base, int dtype, long long elem_off, float* v) {
   if (dtype == DT_BF16) {
@@ -32,12 +39,21 @@ struct GnSrc {
   int dtype;
 };
 
-// partial[((n*chunks + chunk)*C + c)*2 + {0,1}] = sum / sum of squares of channel c over the chunk's pixels
-__global__ void __launch_bounds__(256) gn_partial_kernel(GnSrc s, long long hw, int chunk_px, int chunks, float* partial) {
-  __shared__ float red[8][32][16];
-  const int tx = threadIdx.x, ty = threadIdx.y;
+// Pass 1.  Block = 256 threads = VX channel-vectors (8 channels each) x PY pixel lanes over one chunk of pixels.
+// The block reduces its chunk to per-group (sum, sum of squares) in a fixed order and adds them as doubles to
+// acc[n][group][2] (fp64 atomics: the order-dependent error is ~1e-16 relative, invisible after the fp32 rounding
+// of mean / rstd).  The last block of an image (ticket counter) turns the totals into mean / rstd and zeroes the
+// accumulators and the counter again, so no memset launches are needed.
+template <int VX>
+__global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, long long hw, int chunk_px, int groups, float eps,
+                                                       double* acc, float* stats, unsigned int* counters) {
+  constexpr int PY = 256 / VX;
+  __shared__ float red[PY][VX][16];
+  __shared__ float chan[VX * 8][2];
+  __shared__ unsigned int ticket_s;
+  const int tx = threadIdx.x % VX, ty = threadIdx.x / VX;
   const int C = s.c0 + s.c1;
-  const int v = blockIdx.x * 32 + tx;
+  const int v = blockIdx.x * VX + tx;
   const int chunk = blockIdx.y, n = blockIdx.z;
   const bool active = v * 8 < C;
   float sum[8], sq[8];
@@ -51,7 +67,20 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(GnSrc s, long long hw, 
     const long long p0 = (long long)chunk * chunk_px;
     long long p1 = p0 + chunk_px;
     if (p1 > hw) p1 = hw;
-    for (long long p = p0 + ty; p < p1; p += 8) {
+    long long p = p0 + ty;
+    for (; p + 3 * PY < p1; p += 4 * PY) {          // 4 independent 16-byte loads in flight
+      float x[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; u++) load8(base, s.dtype, ((long long)n * hw + p + u * PY) * ld + ch, x[u]);
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          sum[j] += x[u][j];
+          sq[j] += x[u][j] * x[u][j];
+        }
+    }
+    for (; p < p1; p += PY) {
       float x[8];
       load8(base, s.dtype, ((long long)n * hw + p) * ld + ch, x);
 #pragma unroll
@@ -67,61 +96,71 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(GnSrc s, long long hw, 
     red[ty][tx][8 + j] = sq[j];
   }
   __syncthreads();
-  if (ty == 0 && active) {
-    float* dst = partial + (((long long)n * chunks + chunk) * C + v * 8) * 2;
+  if (ty == 0) {
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       float a = 0.f, b = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; k++) {     // fixed order => deterministic
+      for (int k = 0; k < PY; k++) {     // fixed order
         a += red[k][tx][j];
         b += red[k][tx][8 + j];
       }
-      dst[2 * j] = a;
-      dst[2 * j + 1] = b;
+      chan[tx * 8 + j][0] = a;
+      chan[tx * 8 + j][1] = b;
     }
   }
-}
-
-__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* partial, int chunks, int C, int groups, long long hw,
-                                                          float eps, float* stats) {
-  __shared__ double sh[2][128];
-  const int g = blockIdx.x, n = blockIdx.y;
-  const int cpg = C / groups;
-  const long long entries = (long long)chunks * cpg;
-  double a = 0.0, b = 0.0;
-  for (long long e = threadIdx.x; e < entries; e += 128) {
-    const int chunk = (int)(e / cpg), ch = g * cpg + (int)(e % cpg);
-    const float* src = partial + (((long long)n * chunks + chunk) * C + ch) * 2;
-    a += (double)src[0];
-    b += (double)src[1];
-  }
-  sh[0][threadIdx.x] = a;
-  sh[1][threadIdx.x] = b;
   __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
-      sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+  {
+    const int cpg = C / groups;
+    const int c0 = blockIdx.x * VX * 8;
+    int c1 = c0 + VX * 8;
+    if (c1 > C) c1 = C;
+    const int g_first = c0 / cpg, g_last = (c1 - 1) / cpg;
+    const int g = g_first + (int)threadIdx.x;
+    if (g <= g_last) {
+      int lo = g * cpg, hi = lo + cpg;
+      if (lo < c0) lo = c0;
+      if (hi > c1) hi = c1;
+      float a = 0.f, b = 0.f;
+      for (int c = lo; c < hi; c++) {
+        a += chan[c - c0][0];
+        b += chan[c - c0][1];
+      }
+      atomicAdd(&acc[((long long)n * groups + g) * 2], (double)a);
+      atomicAdd(&acc[((long long)n * groups + g) * 2 + 1], (double)b);
     }
-    __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    const double cnt = (double)hw * cpg;
-    const double mean = sh[0][0] / cnt;
-    double var = sh[1][0] / cnt - mean * mean;
+  // ---- last block of this image finalises
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) ticket_s = atomicAdd(&counters[n], 1u);
+  __syncthreads();
+  if (ticket_s != gridDim.x * gridDim.y - 1) return;
+  __threadfence();
+  if ((int)threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    double* pa = &acc[((long long)n * groups + g) * 2];
+    const double a = __ldcg(pa), b = __ldcg(pa + 1);
+    const double cnt = (double)hw * (C / groups);
+    const double mean = a / cnt;
+    double var = b / cnt - mean * mean;
     if (var < 0.0) var = 0.0;
     stats[((long long)n * groups + g) * 2] = (float)mean;
     stats[((long long)n * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    pa[0] = 0.0;                              // self-cleaning for the next launch
+    pa[1] = 0.0;
   }
+  if (threadIdx.x == 0) counters[n] = 0;
 }
 
+template <int VX>
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, long long hw, int groups, const float* stats,
                                                        const float* gamma, const float* beta, int silu, void* out,
                                                        long long out_ld, int px_per_block) {
-  const int tx = threadIdx.x, ty = threadIdx.y;
+  constexpr int PY = 256 / VX;
+  const int tx = threadIdx.x % VX, ty = threadIdx.x / VX;
   const int C = s.c0 + s.c1;
-  const int v = blockIdx.x * 32 + tx;
+  const int v = blockIdx.x * VX + tx;
   const int n = blockIdx.z;
   if (v * 8 >= C) return;
   const int cpg = C / groups;
@@ -141,7 +180,23 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, long long hw, in
   const long long p0 = (long long)blockIdx.y * px_per_block;
   long long p1 = p0 + px_per_block;
   if (p1 > hw) p1 = hw;
-  for (long long p = p0 + ty; p < p1; p += 8) {
+  long long p = p0 + ty;
+  for (; p + 3 * PY < p1; p += 4 * PY) {
+    float x[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; u++) load8(base, s.dtype, ((long long)n * hw + p + u * PY) * ld + ch, x[u]);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        float y = x[u][j] * sc[j] + sh[j];
+        if (silu) y = __fdividef(y, 1.f + __expf(-y));
+        x[u][j] = y;
+      }
+      store8_bf16(out, ((long long)n * hw + p + u * PY) * out_ld + v * 8, x[u]);
+    }
+  }
+  for (; p < p1; p += PY) {
     float x[8];
     load8(base, s.dtype, ((long long)n * hw + p) * ld + ch, x);
 #pragma unroll
@@ -231,24 +286,30 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* s, long 
 using namespace onedc;
 
 extern "C" int64_t onedc_groupnorm_ws_floats(int32_t n_img, int64_t hw, int32_t c_total) {
-  const int px = gn_chunk_pixels(hw);
-  const int64_t chunks = (hw + px - 1) / px;
-  return (int64_t)n_img * chunks * c_total * 2;
+  (void)hw;
+  (void)c_total;
+  return (int64_t)n_img * 64 * 2;          // fp64 accumulators [n][groups<=64][2], counted in 4-byte units x2
 }
 
 extern "C" int onedc_groupnorm_stats(const void* x0, int32_t c0, int64_t ld0, const void* x1, int32_t c1, int64_t ld1,
                                      int32_t in_dtype, int32_t n_img, int64_t hw, int32_t groups, float eps,
-                                     float* partial, float* stats, void* stream) {
+                                     double* acc, float* stats, uint32_t* counters, void* stream) {
   const int C = c0 + c1;
-  ONEDC_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && C % groups == 0 && ld0 % 8 == 0 && ld1 % 8 == 0, "groupnorm: bad channels");
+  ONEDC_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && C % groups == 0 && ld0 % 8 == 0 && ld1 % 8 == 0 && groups <= 64,
+              "groupnorm: bad channels");
+  ONEDC_CHECK(counters != nullptr && acc != nullptr, "groupnorm: zero-initialised scratch is required");
   GnSrc s{x0, x1, c0, c1, ld0, ld1, in_dtype};
-  const int px = gn_chunk_pixels(hw);
+  const int nvec = C / 8;
+  const int vx = nvec <= 16 ? 16 : 32;
+  const int slabs = (nvec + vx - 1) / vx;
+  const int px = gn_chunk_pixels(hw, slabs);
   const int chunks = (int)((hw + px - 1) / px);
   ONEDC_CHECK(chunks <= 65535 && n_img <= 65535, "groupnorm: grid too large");
-  dim3 grid((C / 8 + 31) / 32, chunks, n_img), block(32, 8);
-  gn_partial_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(s, hw, px, chunks, partial);
-  count_launch();
-  gn_finalize_kernel<<<dim3(groups, n_img), 128, 0, (cudaStream_t)stream>>>(partial, chunks, C, groups, hw, eps, stats);
+  dim3 grid(slabs, chunks, n_img);
+  if (vx == 16)
+    gn_stats_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, px, groups, eps, acc, stats, counters);
+  else
+    gn_stats_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, px, groups, eps, acc, stats, counters);
   count_launch();
   ONEDC_CUDA(cudaGetLastError());
   return 0;
@@ -261,11 +322,17 @@ extern "C" int onedc_groupnorm_apply(const void* x0, int32_t c0, int64_t ld0, co
   const int C = c0 + c1;
   ONEDC_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && C % groups == 0 && out_ld % 8 == 0, "groupnorm: bad channels");
   GnSrc s{x0, x1, c0, c1, ld0, ld1, in_dtype};
-  const int px = hw <= 4096 ? 16 : 64;
+  const int nvec = C / 8;
+  const int px = gn_chunk_pixels(hw, (nvec + (nvec <= 16 ? 15 : 31)) / (nvec <= 16 ? 16 : 32)) ;
   const int chunks = (int)((hw + px - 1) / px);
   ONEDC_CHECK(chunks <= 65535 && n_img <= 65535, "groupnorm: grid too large");
-  dim3 grid((C / 8 + 31) / 32, chunks, n_img), block(32, 8);
-  gn_apply_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(s, hw, groups, stats, gamma, beta, silu, out, out_ld, px);
+  if (nvec <= 16) {
+    dim3 grid((nvec + 15) / 16, chunks, n_img);
+    gn_apply_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, groups, stats, gamma, beta, silu, out, out_ld, px);
+  } else {
+    dim3 grid((nvec + 31) / 32, chunks, n_img);
+    gn_apply_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, groups, stats, gamma, beta, silu, out, out_ld, px);
+  }
   count_launch();
   ONEDC_CUDA(cudaGetLastError());
   return 0;

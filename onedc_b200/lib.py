@@ -26,6 +26,8 @@ class IgemmDesc(C.Structure):
         ("res", C.c_void_p), ("res_dtype", C.c_int32), ("res_ld", C.c_int64),
         ("out", C.c_void_p), ("out_dtype", C.c_int32), ("out_ld", C.c_int64), ("out_col_off", C.c_int32),
         ("store_mode", C.c_int32), ("ps_c", C.c_int32), ("bn", C.c_int32), ("impl", C.c_int32),
+        ("splitk_ws", C.c_void_p), ("splitk_ws_floats", C.c_int64), ("splitk_counters", C.c_void_p),
+        ("splitk_max_tiles", C.c_int32),
     ]
 
 
@@ -39,7 +41,7 @@ PROTOTYPES = {
     "onedc_igemm": (C.c_int, [C.POINTER(IgemmDesc), _vp]),
     "onedc_attention": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
     "onedc_groupnorm_ws_floats": (_i64, [_i32, _i64, _i32]),
-    "onedc_groupnorm_stats": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _vp]),
+    "onedc_groupnorm_stats": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _vp, _vp]),
     "onedc_groupnorm_apply": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _i32,
                                         _vp, _i64, _vp]),
     "onedc_layernorm": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _i64, _vp]),

@@ -100,6 +100,20 @@ def pixshuf_permute(w, b):
     return w[idx], (None if b is None else b[idx])
 
 
+_splitk_scratch = {}
+SPLITK = os.environ.get("ONEDC_SPLITK", "1") == "1"
+
+
+def _splitk_buffers(device):
+    """fp32 partial-tile workspace (148 tiles x 128 x 256) + self-cleaning arrival counters, shared by all launches
+    of a stream (launches are stream-ordered, so one scratch is enough)."""
+    key = str(device)
+    if key not in _splitk_scratch:
+        _splitk_scratch[key] = (torch.empty(160 * 128 * 256, device=device, dtype=torch.float32),
+                                torch.zeros(256, device=device, dtype=torch.int32))
+    return _splitk_scratch[key]
+
+
 def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None, out_dtype=torch.bfloat16,
           store=ST_NORMAL, ps_c=0, w_batched=False, impl=None):
     """out = epilogue(conv(x [cat x2], wt)).  `out` may be a channel-slice view of a wider buffer."""
@@ -149,6 +163,9 @@ def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None
         pr, _, _, _, cr, sr = _nhwc(res)
         d.res, d.res_dtype, d.res_ld = pr, _dt(res), sr
     d.impl = IMPL if impl is None else impl
+    if SPLITK:
+        ws, cnt = _splitk_buffers(x.device)
+        d.splitk_ws, d.splitk_ws_floats, d.splitk_counters, d.splitk_max_tiles = ws.data_ptr(), ws.numel(), cnt.data_ptr(), cnt.numel()
     e0 = _prof_begin()
     L.check(lib.onedc_igemm(C.byref(d), _stream()), "onedc_igemm")
     _prof_end("igemm", e0, 2.0 * n * ho * wo * d.cout * (c0 + c1) * d.ksize * d.ksize)
@@ -196,6 +213,18 @@ def attention_unfused(q, k, vT, out, heads, head_dim, scale=None, valid=None):
     return out
 
 
+_gn_scratch = {}
+
+
+def _gn_buffers(device):
+    """Shared, self-cleaning scratch of the GroupNorm statistics pass (fp64 accumulators + block tickets)."""
+    key = str(device)
+    if key not in _gn_scratch:
+        _gn_scratch[key] = (torch.zeros(256 * 64 * 2, device=device, dtype=torch.float64),
+                            torch.zeros(256, device=device, dtype=torch.int32))
+    return _gn_scratch[key]
+
+
 class GroupNorm:
     def __init__(self, gamma, beta, eps, groups=32, device="cuda"):
         self.gamma = gamma.detach().float().contiguous().to(device)
@@ -209,10 +238,12 @@ class GroupNorm:
         if x2 is not None:
             p1, _, _, _, c1, s1 = _nhwc(x2)
         hw, ct = h * w, c0 + c1
-        ws = torch.empty(int(lib.onedc_groupnorm_ws_floats(n, hw, ct)), device=x.device, dtype=torch.float32)
+        assert n <= 256
+        acc, counters = _gn_buffers(x.device)
         stats = torch.empty((n, self.groups, 2), device=x.device, dtype=torch.float32)
         L.check(lib.onedc_groupnorm_stats(p0, c0, s0, p1, c1, s1, _dt(x), n, hw, self.groups, self.eps,
-                                          ws.data_ptr(), stats.data_ptr(), _stream()), "groupnorm_stats")
+                                          acc.data_ptr(), stats.data_ptr(), counters.data_ptr(), _stream()),
+                "groupnorm_stats")
         if out is None:
             out = torch.empty((n, h, w, ct) if x.dim() == 4 else (n, hw, ct), device=x.device, dtype=torch.bfloat16)
         po, _, _, _, _, so = _nhwc(out)

@@ -152,3 +152,23 @@ def test_large_layer_shapes(cuda):
         out = ops.igemm(x, cw)
         ref = _ref_conv(x, cw.w.float().reshape(3, 3, c, c).permute(2, 3, 0, 1).contiguous(), None, 3, 1)
         _close(out, ref)
+
+
+@pytest.mark.parametrize("h,w,cin,cout,two", [(24, 24, 1280, 1280, False), (12, 12, 1280, 1280, True), (48, 48, 640, 640, False)])
+def test_split_k_small_m_layers(cuda, h, w, cin, cout, two):
+    """UNet 12x12 / 24x24 / 48x48 shapes take the split-K route (few tiles, long K): same result as the SIMT checker
+    and torch, bit-identical run to run (fixed reduction order)."""
+    from onedc_b200 import ops
+    x = _mk((1, h, w, cin), cuda, 1)
+    x2 = _mk((1, h, w, cin), cuda, 5) if two else None
+    ct = cin * (2 if two else 1)
+    wt = _mk((cout, ct, 3, 3), "cpu", 2, scale=(ct * 9) ** -0.5).float()
+    b = _mk((cout,), "cpu", 3).float()
+    res = _mk((1, h, w, cout), cuda, 4)
+    cw = ops.ConvW(wt, b, cuda)
+    out = ops.igemm(x, cw, x2=x2, res=res)
+    out2 = ops.igemm(x, cw, x2=x2, res=res)
+    assert torch.equal(out, out2)
+    ref = _ref_conv(x, cw.w.float().reshape(3, 3, cout, ct).permute(2, 3, 0, 1).contiguous(), b.to(cuda), 3, 1, x2) + res.float()
+    _close(out, ref)
+    _close(ops.igemm(x, cw, x2=x2, res=res, impl=1), ref)
