@@ -64,6 +64,8 @@ extern "C" {
 #define ONEDC_ST_NORMAL 0
 #define ONEDC_ST_PIXSHUF 1    /* PixelShuffle(2): GEMM column q*ps_c + c -> pixel (2y+(q>>1), 2x+(q&1)), channel c */
 #define ONEDC_ST_TRANSPOSED 2 /* out[(img*ncols + col)*out_ld + pixel]  (NCHW / V^T) */
+#define ONEDC_ST_QUAD 3       /* output pixel (2y + (quad>>1), 2x + (quad&1)) of a 2H x 2W image: one phase of a
+                                 nearest-2x-upsample + 3x3 conv folded into four 2x2 convs on the low-res input */
 
 const char* onedc_last_error(void);
 int onedc_version(void);
@@ -102,6 +104,11 @@ typedef struct {
   int64_t splitk_ws_floats;
   void* splitk_counters;
   int32_t splitk_max_tiles; /* number of counters */
+  /* optional custom filter taps (stride 1): ntaps > 0 overrides ksize; tap t reads input pixel
+   * (y + tap_dy[t], x + tap_dx[t]) with weights w_ptr[t]; `quad` selects the ONEDC_ST_QUAD phase */
+  int32_t ntaps;
+  int32_t tap_dy[9], tap_dx[9];
+  int32_t quad;
 } onedc_igemm_desc;
 
 int onedc_igemm(const onedc_igemm_desc* d, void* stream);

@@ -145,25 +145,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       tmem_ld32(tmem_base + lane_off + st * BKV + 32, sr + 32);
       tmem_ld_wait();
       const int nvalid = p.skv - j * BKV;            // columns >= nvalid are zero-filled padding keys
+      if (nvalid < BKV) {                            // only the last block can be partial (uniform branch)
+#pragma unroll
+        for (int c = 0; c < BKV; c++)
+          if (c >= nvalid) sr[c] = 0xff800000u;      // -inf
+      }
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < BKV; c++) {
-        float s = __uint_as_float(sr[c]) * p.scale_log2;
-        if (c >= nvalid) s = -INFINITY;
-        sr[c] = __float_as_uint(s);
-        mx = fmaxf(mx, s);
-      }
-      const float m_new = fmaxf(m_run, mx);
+      for (int c = 0; c < BKV; c++) mx = fmaxf(mx, __uint_as_float(sr[c]));
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);     // scale > 0: max commutes with the scaling
       const float alpha = exp2f(m_run - m_new);      // 0 on the first block (m_run = -inf)
       float rs = 0.f;
       uint32_t pk[BKV / 2];
 #pragma unroll
       for (int c = 0; c < BKV; c += 2) {
-        const float e0 = exp2f(__uint_as_float(sr[c]) - m_new);
-        const float e1 = exp2f(__uint_as_float(sr[c + 1]) - m_new);
+        // exp(s*scale - m) as one FFMA + one EX2 per element
+        const float e0 = exp2f(fmaf(__uint_as_float(sr[c]), p.scale_log2, -m_new));
+        const float e1 = exp2f(fmaf(__uint_as_float(sr[c + 1]), p.scale_log2, -m_new));
         pk[c >> 1] = pack_bf16x2(e0, e1);
-        // accumulate what the MMA will actually see (bf16-rounded probabilities)
-        rs += bf16lo(pk[c >> 1]) + bf16hi(pk[c >> 1]);
+        rs += e0 + e1;
       }
       l_run = l_run * alpha + rs;
       // P buffer is free and O is final for block j-1 once PV(j-1) has completed
@@ -277,7 +277,7 @@ extern "C" int onedc_attention(const void* q, int64_t q_ld, const void* k, const
                                float scale, int32_t impl, void* stream) {
   ONEDC_CHECK(head_dim % 8 == 0 && head_dim >= 8 && head_dim <= 192, "attention: head_dim must be a multiple of 8, <= 192");
   ONEDC_CHECK(q_ld % 8 == 0 && kv_ld % 8 == 0 && o_ld % 8 == 0, "attention: leading dims must be multiples of 8");
-  ONEDC_CHECK(sq > 0 && skv > 0, "attention: empty sequence");
+  ONEDC_CHECK(sq > 0 && skv > 0 && scale > 0.f, "attention: empty sequence or non-positive scale");
   cudaStream_t st = (cudaStream_t)stream;
   if (impl == 1) {
     const long long total = (long long)batch * heads * sq;

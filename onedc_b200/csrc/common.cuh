@@ -11,7 +11,7 @@ namespace onedc {
 enum DType { DT_BF16 = 0, DT_F32 = 1 };
 enum Act { ACT_NONE = 0, ACT_LRELU = 1, ACT_SILU = 2, ACT_GELU = 3 };
 enum EpiMode { EPI_PLAIN = 0, EPI_PAIR_LRELU = 1, EPI_GEGLU = 2 };
-enum StoreMode { ST_NORMAL = 0, ST_PIXSHUF = 1, ST_TRANSPOSED = 2 };
+enum StoreMode { ST_NORMAL = 0, ST_PIXSHUF = 1, ST_TRANSPOSED = 2, ST_QUAD = 3 };
 
 // error handling: every C-ABI entry returns 0 or a negative code; message via onedc_last_error().
 void set_error(const char* fmt, ...);

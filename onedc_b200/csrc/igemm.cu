@@ -53,7 +53,7 @@ struct IgemmParams {
   void* out;
   int out_dtype;
   long long out_ld;
-  int out_col_off, store_mode, ps_c;
+  int out_col_off, store_mode, ps_c, quad;
   int ncols_out;          // cout (plain) or cout/2 (pair modes)
   int vec_ok;
   // split-K (small-M layers): fp32 partial tiles + per-tile arrival counters
@@ -135,6 +135,8 @@ __device__ __forceinline__ void epilogue16(const IgemmParams& p, int img, int y,
     int q = ocol / p.ps_c;
     oc = ocol - q * p.ps_c;
     opix = ((long long)img * (2 * p.H) + (2 * y + (q >> 1))) * (2 * p.W) + (2 * x + (q & 1));
+  } else if (p.store_mode == ST_QUAD) {
+    opix = ((long long)img * (2 * p.H) + (2 * y + (p.quad >> 1))) * (2 * p.W) + (2 * x + (p.quad & 1));
   }
   const long long o = opix * p.out_ld + p.out_col_off + oc;
   if (p.out_dtype == DT_BF16) {
@@ -257,6 +259,8 @@ __device__ __forceinline__ void epi_finish32(const IgemmParams& p, float* a, con
     const int qd = ocol / p.ps_c;
     oc = ocol - qd * p.ps_c;
     opix = ((long long)img * (2 * p.H) + (2 * y + (qd >> 1))) * (2 * p.W) + (2 * x + (qd & 1));
+  } else if (p.store_mode == ST_QUAD) {
+    opix = ((long long)img * (2 * p.H) + (2 * y + (p.quad >> 1))) * (2 * p.W) + (2 * x + (p.quad & 1));
   }
   const long long o = opix * p.out_ld + p.out_col_off + oc;
   if (p.out_dtype == DT_BF16) {
@@ -427,7 +431,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       const int o0 = t.n_tile * out_cols_tile;         // first output column of this tile
       const long long pix = ((long long)t.img * p.H + y) * p.W + x;
       const bool fast = p.vec_ok && (o0 + out_cols_tile <= p.ncols_out) && (out_cols_tile % 32 == 0) &&
-                        (p.store_mode == ST_NORMAL || (p.store_mode == ST_PIXSHUF && p.ps_c % 32 == 0));
+                        (p.store_mode == ST_NORMAL || p.store_mode == ST_QUAD || (p.store_mode == ST_PIXSHUF && p.ps_c % 32 == 0));
       if (SPLITK) {
         // ---- split-K (one work item per CTA, all co-resident): park the raw fp32 accumulators, wait until all
         //      splits of this tile have done so, then reduce a row slice of the tile in split order (deterministic)
@@ -578,10 +582,13 @@ __device__ __forceinline__ void simt_dot16(const IgemmParams& p, int img, int y,
   for (int j = 0; j < 16; j++) acc[j] = 0.f;
   const int taps = p.taps;
   for (int tap = 0; tap < taps; tap++) {
-    int iy = y, ix = x;
-    if (p.ksize == 3) {
-      iy = y * p.stride + tap / 3 - 1;
-      ix = x * p.stride + tap % 3 - 1;
+    int iy, ix;
+    if (p.stride == 2) {
+      iy = y * 2 + tap / 3 - 1;
+      ix = x * 2 + tap % 3 - 1;
+    } else {
+      iy = y + p.tap_dy[tap];
+      ix = x + p.tap_dx[tap];
     }
     if (iy < 0 || iy >= p.h_in || ix < 0 || ix >= p.w_in) continue;
     const long long ipix = ((long long)img * p.h_in + iy) * p.w_in + ix;
@@ -748,7 +755,9 @@ static int igemm_launch(const onedc_igemm_desc* d, cudaStream_t stream) {
   p.tiles_y = (p.H + p.TH - 1) / p.TH;
   p.tiles_x = (p.W + p.TW - 1) / p.TW;
   p.m_tiles = p.n_img * p.tiles_y * p.tiles_x;
-  p.taps = d->ksize * d->ksize;
+  p.taps = d->ntaps > 0 ? d->ntaps : d->ksize * d->ksize;
+  ONEDC_CHECK(p.taps <= 9 && !(d->ntaps > 0 && d->stride != 1), "igemm: custom taps need stride 1 and at most 9 taps");
+  p.quad = d->quad;
   p.kchunks[0] = (d->a_c[0] + 63) / 64;
   p.kchunks[1] = (d->a_c[1] + 63) / 64;
   p.c1_off = d->a_c[0];
@@ -756,7 +765,12 @@ static int igemm_launch(const onedc_igemm_desc* d, cudaStream_t stream) {
   ONEDC_CHECK(!(d->w_batched && p.taps != 1), "igemm: batched weights need a 1x1 kernel");
   for (int t = 0; t < p.taps; t++) {
     int ky = t / 3, kx = t % 3;
-    if (d->ksize == 1) {
+    if (d->ntaps > 0) {
+      p.tap_dc[t] = 0;
+      p.tap_dp[t] = 0;
+      p.tap_dx[t] = d->tap_dx[t];
+      p.tap_dy[t] = d->tap_dy[t];
+    } else if (d->ksize == 1) {
       p.tap_dc[t] = p.tap_dx[t] = p.tap_dp[t] = p.tap_dy[t] = 0;
     } else if (d->stride == 1) {
       p.tap_dc[t] = 0;
@@ -821,7 +835,7 @@ static int igemm_launch(const onedc_igemm_desc* d, cudaStream_t stream) {
     const int kiters = p.taps * (p.kchunks[0] + p.kchunks[1]);
     const int octile = pair ? p.BN / 2 : p.BN;
     const bool fast_all = p.vec_ok && (d->cout % p.BN == 0) && (octile % 32 == 0) &&
-                          (d->store_mode == ST_NORMAL || (d->store_mode == ST_PIXSHUF && d->ps_c % 32 == 0));
+                          (d->store_mode == ST_NORMAL || d->store_mode == ST_QUAD || (d->store_mode == ST_PIXSHUF && d->ps_c % 32 == 0));
     if (d->impl == 0 && p.ws != nullptr && p.counters != nullptr && fast_all && tiles * 2 <= sm_count() &&
         kiters >= 16 && tiles <= d->splitk_max_tiles / 2) {
       int s = sm_count() / tiles;

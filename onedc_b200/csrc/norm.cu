@@ -6,9 +6,11 @@
 
 namespace onedc {
 
-// pixels per block of the statistics pass: ~4 blocks per SM on big tensors, >= 16 pixels on small ones
-__host__ __device__ inline int gn_chunk_pixels(long long hw, int slabs) {
-  long long target = 592 / (slabs > 0 ? slabs : 1);
+// pixels per block of the statistics / apply passes.  Small tensors: about one block per SM (every block ends
+// with same-address atomics, which serialise); big streaming tensors: ~4 blocks per SM to cover HBM latency.
+__host__ __device__ inline int gn_chunk_pixels(long long hw, int slabs, int c_total) {
+  const long long bytes = hw * c_total * 2;
+  long long target = (bytes >= (64ll << 20) ? 592 : (bytes >= (8ll << 20) ? 296 : 148)) / (slabs > 0 ? slabs : 1);
   if (target < 1) target = 1;
   long long p = (hw + target - 1) / target;
   p = (p + 15) / 16 * 16;
@@ -302,7 +304,7 @@ extern "C" int onedc_groupnorm_stats(const void* x0, int32_t c0, int64_t ld0, co
   const int nvec = C / 8;
   const int vx = nvec <= 16 ? 16 : 32;
   const int slabs = (nvec + vx - 1) / vx;
-  const int px = gn_chunk_pixels(hw, slabs);
+  const int px = gn_chunk_pixels(hw, slabs, C);
   const int chunks = (int)((hw + px - 1) / px);
   ONEDC_CHECK(chunks <= 65535 && n_img <= 65535, "groupnorm: grid too large");
   dim3 grid(slabs, chunks, n_img);
@@ -323,7 +325,7 @@ extern "C" int onedc_groupnorm_apply(const void* x0, int32_t c0, int64_t ld0, co
   ONEDC_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && C % groups == 0 && out_ld % 8 == 0, "groupnorm: bad channels");
   GnSrc s{x0, x1, c0, c1, ld0, ld1, in_dtype};
   const int nvec = C / 8;
-  const int px = gn_chunk_pixels(hw, (nvec + (nvec <= 16 ? 15 : 31)) / (nvec <= 16 ? 16 : 32)) ;
+  const int px = gn_chunk_pixels(hw, (nvec + (nvec <= 16 ? 15 : 31)) / (nvec <= 16 ? 16 : 32), C);
   const int chunks = (int)((hw + px - 1) / px);
   ONEDC_CHECK(chunks <= 65535 && n_img <= 65535, "groupnorm: grid too large");
   if (nvec <= 16) {

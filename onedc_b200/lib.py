@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libonedc_b200.so")
 BF16, F32 = 0, 1
 ACT_NONE, ACT_LRELU, ACT_SILU, ACT_GELU = 0, 1, 2, 3
 EPI_PLAIN, EPI_PAIR_LRELU, EPI_GEGLU = 0, 1, 2
-ST_NORMAL, ST_PIXSHUF, ST_TRANSPOSED = 0, 1, 2
+ST_NORMAL, ST_PIXSHUF, ST_TRANSPOSED, ST_QUAD = 0, 1, 2, 3
 
 
 class IgemmDesc(C.Structure):
@@ -28,6 +28,7 @@ class IgemmDesc(C.Structure):
         ("store_mode", C.c_int32), ("ps_c", C.c_int32), ("bn", C.c_int32), ("impl", C.c_int32),
         ("splitk_ws", C.c_void_p), ("splitk_ws_floats", C.c_int64), ("splitk_counters", C.c_void_p),
         ("splitk_max_tiles", C.c_int32),
+        ("ntaps", C.c_int32), ("tap_dy", C.c_int32 * 9), ("tap_dx", C.c_int32 * 9), ("quad", C.c_int32),
     ]
 
 

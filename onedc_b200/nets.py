@@ -16,7 +16,8 @@ import math
 import torch
 
 from . import ops
-from .ops import (ACT_LRELU, ACT_NONE, ConvW, DepthwiseW, GroupNorm, LayerNorm, igemm, pair_permute, pixshuf_permute)
+from .ops import (ACT_LRELU, ACT_NONE, ConvW, DepthwiseW, GroupNorm, LayerNorm, UpConv, igemm, pair_permute,
+                  pixshuf_permute)
 from .lib import EPI_GEGLU, EPI_PAIR_LRELU, ST_PIXSHUF, ST_TRANSPOSED
 from .weights import merge_lora
 
@@ -323,7 +324,7 @@ class UNet:
             if i > 0:
                 blk["attn"] = [UNetTransformer(sd, f"up_blocks.{i}.attentions.{j}", c, dev) for j in range(3)]
             if i < 3:
-                blk["up"] = ConvW(*_wb(sd, f"up_blocks.{i}.upsamplers.0.conv"), dev)
+                blk["up"] = UpConv(*_wb(sd, f"up_blocks.{i}.upsamplers.0.conv"), dev)
             self.up.append(blk)
         self.norm_out = GroupNorm(sd["conv_norm_out.weight"], sd["conv_norm_out.bias"], 1e-5, device=dev)
         self.conv_out = ConvW(*_wb(sd, "conv_out"), dev)
@@ -360,7 +361,7 @@ class UNet:
                 if "attn" in blk:
                     h = blk["attn"][j](h, ctx)
             if "up" in blk:
-                h = igemm(ops.upsample2x(h), blk["up"])
+                h = blk["up"](h)
         eps = igemm(self.norm_out(h), self.conv_out, out_dtype=f32)
         return eps, reduced
 
@@ -439,7 +440,7 @@ class VAEDecoder:
             for j in range(3):
                 res.append(VAERes(sd, f"{d}.up_blocks.{i}.resnets.{j}", prev, c, dev))
                 prev = c
-            up = ConvW(*_wb(sd, f"{d}.up_blocks.{i}.upsamplers.0.conv"), dev) if i < 3 else None
+            up = UpConv(*_wb(sd, f"{d}.up_blocks.{i}.upsamplers.0.conv"), dev) if i < 3 else None
             self.ups.append((res, up))
         self.norm_out = GroupNorm(sd[d + ".conv_norm_out.weight"], sd[d + ".conv_norm_out.bias"], 1e-6, device=dev)
         self.conv_out = ConvW(*_wb(sd, d + ".conv_out"), dev)
@@ -456,7 +457,7 @@ class VAEDecoder:
             for r in res:
                 t = r(t)
             if up is not None:
-                t = igemm(ops.upsample2x(t), up)
+                t = up(t)
         # NCHW fp32 image straight out of the last conv's epilogue
         img = igemm(self.norm_out(t), self.conv_out, store=ST_TRANSPOSED, out_dtype=torch.float32)
         return img.view(n, 3, 8 * h, 8 * w)

@@ -9,7 +9,7 @@ import torch
 
 from . import lib as L
 from .lib import (ACT_GELU, ACT_LRELU, ACT_NONE, ACT_SILU, BF16, EPI_GEGLU, EPI_PAIR_LRELU, EPI_PLAIN, F32,
-                  ST_NORMAL, ST_PIXSHUF, ST_TRANSPOSED)
+                  ST_NORMAL, ST_PIXSHUF, ST_QUAD, ST_TRANSPOSED)
 
 # 0 = tcgen05 kernels (product).  1 = SIMT checking kernels; tests flip this to cross-check on the GPU.
 IMPL = int(os.environ.get("ONEDC_IMPL", "0"))
@@ -76,6 +76,48 @@ class ConvW:
         self.bias = None if bias is None else bias.detach().float().contiguous().to(device)
         self.epi, self.bn = epi, bn
         self.ncols = cout // 2 if epi != EPI_PLAIN else cout
+        self.taps = None                          # custom (dy, dx) taps; None = dense k x k
+
+    @classmethod
+    def from_taps(cls, w_taps, taps, bias=None, device="cuda"):
+        """w_taps: fp32 [ntaps, cout, cin]; taps: list of (dy, dx) input offsets (stride 1)."""
+        self = cls.__new__(cls)
+        nt, cout, cin = w_taps.shape
+        assert cin % 8 == 0 and nt == len(taps) <= 9
+        self.ksize, self.cout, self.ktot = 1, cout, cin
+        self.w = w_taps.contiguous().to(device=device, dtype=torch.bfloat16)
+        self.bias = None if bias is None else bias.detach().float().contiguous().to(device)
+        self.epi, self.bn, self.ncols, self.taps = EPI_PLAIN, 0, cout, list(taps)
+        return self
+
+
+class UpConv:
+    """nearest-2x upsample followed by a 3x3 conv (diffusers Upsample2D), folded: output phase (a, b) =
+    (row parity, column parity) only ever sees 2x2 distinct input pixels, so it is a 4-tap conv on the LOW-RES
+    input with pre-summed weights -- 16 instead of 36 multiply-adds per output pixel and no upsampled tensor.
+      a = 0: rows {y-1: W[0], y: W[1]+W[2]}      a = 1: rows {y: W[0]+W[1], y+1: W[2]}     (same for columns)
+    Zero padding of the upsampled image maps to out-of-bounds (zero-filled) low-res pixels."""
+
+    def __init__(self, w, b, device="cuda"):
+        w = w.float()                                            # [cout, cin, 3, 3]
+        self.cout = w.shape[0]
+        sets = {0: [(-1, [0]), (0, [1, 2])], 1: [(0, [0, 1]), (1, [2])]}
+        self.quads = []
+        for a in (0, 1):
+            for bb in (0, 1):
+                taps, ws = [], []
+                for dy, kys in sets[a]:
+                    for dx, kxs in sets[bb]:
+                        taps.append((dy, dx))
+                        ws.append(sum(w[:, :, ky, kx] for ky in kys for kx in kxs))
+                self.quads.append(ConvW.from_taps(torch.stack(ws, 0), taps, b, device))
+
+    def __call__(self, x):
+        n, h, w, c = x.shape
+        out = torch.empty((n, 2 * h, 2 * w, self.cout), device=x.device, dtype=torch.bfloat16)
+        for q, cw in enumerate(self.quads):
+            igemm(x, cw, out=out, store=ST_QUAD, quad=q)
+        return out
 
 
 def pair_permute(w, b, bn=256):
@@ -115,7 +157,7 @@ def _splitk_buffers(device):
 
 
 def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None, out_dtype=torch.bfloat16,
-          store=ST_NORMAL, ps_c=0, w_batched=False, impl=None):
+          store=ST_NORMAL, ps_c=0, w_batched=False, impl=None, quad=0):
     """out = epilogue(conv(x [cat x2], wt)).  `out` may be a channel-slice view of a wider buffer."""
     lib = L.load()
     d = L.IgemmDesc()
@@ -135,6 +177,10 @@ def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None
         d.bias = None if wt.bias is None else wt.bias.data_ptr()
         d.epi_mode, d.bn = wt.epi, wt.bn
         ncols = wt.ncols
+        if wt.taps is not None:
+            d.ntaps = len(wt.taps)
+            for i, (dy, dx) in enumerate(wt.taps):
+                d.tap_dy[i], d.tap_dx[i] = dy, dx
     else:                                   # (tensor [z, rows, k] view, ...) used as a batched B operand
         bt = wt
         assert bt.dim() == 3 and bt.stride(2) == 1
@@ -146,6 +192,7 @@ def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None
     d.act, d.slope = act, slope
     ho, wo = (h // 2, w // 2) if stride == 2 else (h, w)
     if out is None:
+        assert store != ST_QUAD, "ST_QUAD needs a caller-provided full-resolution output"
         if store == ST_PIXSHUF:
             out = torch.empty((n, 2 * ho, 2 * wo, ps_c), device=x.device, dtype=out_dtype)
         elif store == ST_TRANSPOSED:
@@ -158,7 +205,7 @@ def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None
     else:
         po, no, hoo, woo, co, so = _nhwc(out)
         d.out, d.out_ld, d.out_col_off = po, so, 0
-    d.out_dtype, d.store_mode, d.ps_c = _dt(out), store, ps_c
+    d.out_dtype, d.store_mode, d.ps_c, d.quad = _dt(out), store, ps_c, quad
     if res is not None:
         pr, _, _, _, cr, sr = _nhwc(res)
         d.res, d.res_dtype, d.res_ld = pr, _dt(res), sr
@@ -168,7 +215,7 @@ def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None
         d.splitk_ws, d.splitk_ws_floats, d.splitk_counters, d.splitk_max_tiles = ws.data_ptr(), ws.numel(), cnt.data_ptr(), cnt.numel()
     e0 = _prof_begin()
     L.check(lib.onedc_igemm(C.byref(d), _stream()), "onedc_igemm")
-    _prof_end("igemm", e0, 2.0 * n * ho * wo * d.cout * (c0 + c1) * d.ksize * d.ksize)
+    _prof_end("igemm", e0, 2.0 * n * ho * wo * d.cout * (c0 + c1) * (d.ntaps if d.ntaps > 0 else d.ksize * d.ksize))
     return out
 
 

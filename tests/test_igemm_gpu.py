@@ -172,3 +172,25 @@ def test_split_k_small_m_layers(cuda, h, w, cin, cout, two):
     ref = _ref_conv(x, cw.w.float().reshape(3, 3, cout, ct).permute(2, 3, 0, 1).contiguous(), b.to(cuda), 3, 1, x2) + res.float()
     _close(out, ref)
     _close(ops.igemm(x, cw, x2=x2, res=res, impl=1), ref)
+
+
+@pytest.mark.parametrize("n,h,w,c,co", [(1, 24, 24, 256, 256), (2, 12, 20, 512, 512), (1, 48, 48, 1280, 1280)])
+def test_folded_upsample_conv(cuda, n, h, w, c, co):
+    """nearest-2x + conv3x3 folded into four 4-tap convs on the low-res input == the unfolded computation."""
+    from onedc_b200 import ops
+    x = _mk((n, h, w, c), cuda, 1)
+    wt = _mk((co, c, 3, 3), "cpu", 2, scale=(c * 9) ** -0.5).float()
+    b = _mk((co,), "cpu", 3).float()
+    up = ops.UpConv(wt, b, cuda)
+    out = up(x)
+    xu = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(xu, wt.to(cuda), b.to(cuda), padding=1).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    _close(out, ref)
+    # and the unfolded kernel route agrees too
+    ref2 = ops.igemm(ops.upsample2x(x), ops.ConvW(wt, b, cuda))
+    _close(out, ref2.float())
+    cw = up.quads[3]
+    o1 = torch.zeros_like(out)
+    ops.igemm(x, cw, out=o1, store=ops.ST_QUAD, quad=3, impl=1)
+    _close(o1[:, 1::2, 1::2], ref[:, 1::2, 1::2])
