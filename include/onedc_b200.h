@@ -120,12 +120,13 @@ int onedc_attention(const void* q, int64_t q_ld, const void* k, const void* v, i
                     float scale, int32_t impl, void* stream);
 
 /* ---- normalisation / elementwise --------------------------------------------------------- */
-/* GroupNorm over the channel concatenation of up to two NHWC sources. acc: fp64 scratch [n_img][groups][2]
- * (onedc_groupnorm_ws_floats() floats) and counters: n_img uint32 -- both zero on entry and zero again on exit
- * (the last block of an image finalises and cleans up); stats: fp32 [n_img][groups][2] (mean, rstd). */
+/* GroupNorm over the channel concatenation of up to two NHWC sources. partial: fp32 scratch of
+ * onedc_groupnorm_ws_floats() floats (per-block group sums); counters: n_img uint32, zero on entry and zero again
+ * on exit (the last block of an image merges the block sums in a fixed order); stats: fp32 [n_img][groups][2]
+ * (mean, rstd). */
 int64_t onedc_groupnorm_ws_floats(int32_t n_img, int64_t hw, int32_t c_total);
 int onedc_groupnorm_stats(const void* x0, int32_t c0, int64_t ld0, const void* x1, int32_t c1, int64_t ld1,
-                          int32_t in_dtype, int32_t n_img, int64_t hw, int32_t groups, float eps, double* acc,
+                          int32_t in_dtype, int32_t n_img, int64_t hw, int32_t groups, float eps, float* partial,
                           float* stats, uint32_t* counters, void* stream);
 int onedc_groupnorm_apply(const void* x0, int32_t c0, int64_t ld0, const void* x1, int32_t c1, int64_t ld1,
                           int32_t in_dtype, int32_t n_img, int64_t hw, int32_t groups, const float* stats,
@@ -154,10 +155,12 @@ int onedc_x0_prepare(const float* reduced, const float* eps, float sqrt_alpha, f
                      int64_t pixels, void* stream);
 
 /* ---- entropy-index kernels --------------------------------------------------------------- */
-/* lut: device uint8[65536] (bf16 bit pattern -> index).  scales: NHWC [n,h,w,c4*4] with pixel stride ld.
+/* lut: device uint8[65536] (bf16 bit pattern -> index); [lut_lo, lut_hi) = the positive bit patterns whose index is
+ * neither 0 nor 255 (first pattern with index > 0, first pattern with index 255): the kernel keeps only that slice
+ * in shared memory.  scales: NHWC [n,h,w,c4*4] with pixel stride ld.
  * idx_out: int16 [n][c4][h][w]  (the symbol order of the y stream). */
-int onedc_scale_to_index(const void* scales, int64_t ld, const uint8_t* lut, int16_t* idx_out, int32_t step,
-                         int32_t n_img, int32_t h, int32_t w, int32_t c4, void* stream);
+int onedc_scale_to_index(const void* scales, int64_t ld, const uint8_t* lut, int32_t lut_lo, int32_t lut_hi,
+                         int16_t* idx_out, int32_t step, int32_t n_img, int32_t h, int32_t w, int32_t c4, void* stream);
 /* generic build_indexes: in_dtype bf16 -> LUT, fp32 -> 255 ascending thresholds (device fp32[255]) */
 int onedc_build_indexes(const void* scales, int32_t in_dtype, const uint8_t* lut, const float* thresholds,
                         int32_t* idx_out, int64_t n, void* stream);

@@ -12,32 +12,58 @@ __device__ __constant__ int kXor[4] = {0, 3, 2, 1};
 
 // ------------------------------------------------------------------------------------------------
 // scales (NHWC bf16, 4*c4 channels) -> int16 CDF indices in stream order [n][c4][h*w].
-// Block = 128 consecutive pixels of one image: gather the active c4-channel slice (contiguous 2*c4 bytes
-// per pixel), LUT each value, transpose through shared memory, write 256 contiguous bytes per plane.
+// Block = 128 consecutive pixels of one image.  Phase 1 (thread = pixel): four 16-byte loads of the active
+// c4-channel slice, table lookup, indices to shared memory.  Phase 2 (thread = plane quarter): 16-byte
+// stores of 8 consecutive pixels of one plane, so every global access of the kernel is a full 16-byte vector.
+// The lookup uses the compact table: only bf16 patterns in [lo, hi) have an index other than 0 / 255
+// (lo = first pattern with index > 0, hi = first pattern with index 255), ~1.2 KB instead of 64 KB.
 template <int C4>
 __global__ void __launch_bounds__(128) scale_to_index_kernel(const __nv_bfloat16* scales, long long ld, const uint8_t* lut,
-                                                             int16_t* idx_out, int step, int h, int w) {
-  __shared__ int16_t tile[C4][128 + 2];
+                                                             int lo, int hi, int16_t* idx_out, int step, int h, int w) {
+  __shared__ __align__(16) int16_t tile[C4][128 + 8];
+  __shared__ uint8_t tab[2048];
   const long long hw = (long long)h * w;
   const int n = blockIdx.y;
-  const long long p = (long long)blockIdx.x * 128 + threadIdx.x;
+  const long long p0 = (long long)blockIdx.x * 128;
+  const long long p = p0 + threadIdx.x;
+  const int span = hi - lo;
+  for (int i = threadIdx.x; i < span; i += 128) tab[i] = __ldg(lut + lo + i);
+  __syncthreads();
   if (p < hw) {
     const int y = (int)(p / w), x = (int)(p - (long long)y * w);
     const int g = (2 * (y & 1) + (x & 1)) ^ kXor[step];
     const uint4* src = reinterpret_cast<const uint4*>(scales + ((long long)n * hw + p) * ld + g * C4);
+    uint4 q[C4 / 8];
+#pragma unroll
+    for (int v = 0; v < C4 / 8; v++) q[v] = __ldg(src + v);
 #pragma unroll
     for (int v = 0; v < C4 / 8; v++) {
-      uint4 q = __ldg(src + v);
-      uint32_t wds[4] = {q.x, q.y, q.z, q.w};
+      const uint32_t wds[4] = {q[v].x, q[v].y, q[v].z, q[v].w};
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        tile[v * 8 + 2 * j][threadIdx.x] = (int16_t)__ldg(lut + (wds[j] & 0xFFFFu));
-        tile[v * 8 + 2 * j + 1][threadIdx.x] = (int16_t)__ldg(lut + (wds[j] >> 16));
+#pragma unroll
+        for (int hlf = 0; hlf < 2; hlf++) {
+          const int bits = hlf ? (int)(wds[j] >> 16) : (int)(wds[j] & 0xFFFFu);   // sign bit set => >= 0x8000 => 0
+          int r = 0;
+          if (bits >= hi && bits <= 0x7F80) r = 255;          // NaN patterns (> 0x7F80) keep index 0 like the table
+          else if (bits >= lo && bits < hi) r = tab[bits - lo];
+          tile[v * 8 + 2 * j + hlf][threadIdx.x] = (int16_t)r;
+        }
       }
     }
   }
   __syncthreads();
-  if (p < hw) {
+  if ((hw & 7) == 0 && p0 + 128 <= hw) {
+    // thread = (plane c, 32-pixel quarter): 4 x 16-byte stores
+#pragma unroll
+    for (int r = 0; r < C4 / 32; r++) {
+      const int c = r * 32 + (threadIdx.x >> 2), qx = (threadIdx.x & 3) * 32;
+      const uint4* s4 = reinterpret_cast<const uint4*>(&tile[c][qx]);
+      uint4* d4 = reinterpret_cast<uint4*>(idx_out + ((long long)n * C4 + c) * hw + p0 + qx);
+#pragma unroll
+      for (int i = 0; i < 4; i++) d4[i] = s4[i];
+    }
+  } else if (p < hw) {
     int16_t* dst = idx_out + (long long)n * C4 * hw + p;
 #pragma unroll 8
     for (int c = 0; c < C4; c++) dst[(long long)c * hw] = tile[c][threadIdx.x];
@@ -69,17 +95,30 @@ template <int C4, int MODE>
 __global__ void __launch_bounds__(128) dequant_kernel(int16_t* sym, const __nv_bfloat16* yin, long long yin_ld,
                                                       const __nv_bfloat16* means, long long means_ld, __nv_bfloat16* y_hat,
                                                       long long y_ld, int step, int h, int w) {
-  __shared__ int16_t tile[C4][128 + 2];
+  __shared__ __align__(16) int16_t tile[C4][128 + 8];
   const long long hw = (long long)h * w;
   const int n = blockIdx.y;
   const long long p = (long long)blockIdx.x * 128 + threadIdx.x;
   const bool ok = p < hw;
-  if (MODE == 0 && sym != nullptr && ok) {
-    const int16_t* src = sym + (long long)n * C4 * hw + p;
+  const long long p0 = (long long)blockIdx.x * 128;
+  const bool vec = ((hw & 7) == 0) && (p0 + 128 <= hw);
+  if (MODE == 0 && sym != nullptr) {
+    if (vec) {
+#pragma unroll
+      for (int r = 0; r < C4 / 32; r++) {       // thread = (plane c, 32-pixel quarter): 4 x 16-byte loads
+        const int c = r * 32 + (threadIdx.x >> 2), qx = (threadIdx.x & 3) * 32;
+        const uint4* s4 = reinterpret_cast<const uint4*>(sym + ((long long)n * C4 + c) * hw + p0 + qx);
+        uint4* d4 = reinterpret_cast<uint4*>(&tile[c][qx]);
+#pragma unroll
+        for (int i = 0; i < 4; i++) d4[i] = __ldg(s4 + i);
+      }
+    } else if (ok) {
+      const int16_t* src = sym + (long long)n * C4 * hw + p;
 #pragma unroll 8
-    for (int c = 0; c < C4; c++) tile[c][threadIdx.x] = src[(long long)c * hw];
+      for (int c = 0; c < C4; c++) tile[c][threadIdx.x] = src[(long long)c * hw];
+    }
+    __syncthreads();
   }
-  // (each thread only touches its own column of the tile, no barrier needed in MODE 0)
   if (ok) {
     const int y = (int)(p / w), x = (int)(p - (long long)y * w);
     const int g = (2 * (y & 1) + (x & 1)) ^ kXor[step];
@@ -126,7 +165,19 @@ __global__ void __launch_bounds__(128) dequant_kernel(int16_t* sym, const __nv_b
         for (int v = 0; v < C4 / 8; v++) z[v] = make_uint4(0, 0, 0, 0);
       }
     }
-    if (MODE == 1) {
+  }
+  if (MODE == 1) {
+    __syncthreads();
+    if (vec) {
+#pragma unroll
+      for (int r = 0; r < C4 / 32; r++) {
+        const int c = r * 32 + (threadIdx.x >> 2), qx = (threadIdx.x & 3) * 32;
+        const uint4* s4 = reinterpret_cast<const uint4*>(&tile[c][qx]);
+        uint4* d4 = reinterpret_cast<uint4*>(sym + ((long long)n * C4 + c) * hw + p0 + qx);
+#pragma unroll
+        for (int i = 0; i < 4; i++) d4[i] = s4[i];
+      }
+    } else if (ok) {
       int16_t* o = sym + (long long)n * C4 * hw + p;
 #pragma unroll 8
       for (int c = 0; c < C4; c++) o[(long long)c * hw] = tile[c][threadIdx.x];
@@ -293,13 +344,17 @@ static inline int ew_blocks(long long total, int threads) {
 
 using namespace onedc;
 
-extern "C" int onedc_scale_to_index(const void* scales, int64_t ld, const uint8_t* lut, int16_t* idx_out, int32_t step,
-                                    int32_t n_img, int32_t h, int32_t w, int32_t c4, void* stream) {
+extern "C" int onedc_scale_to_index(const void* scales, int64_t ld, const uint8_t* lut, int32_t lut_lo, int32_t lut_hi,
+                                    int16_t* idx_out, int32_t step, int32_t n_img, int32_t h, int32_t w, int32_t c4,
+                                    void* stream) {
   ONEDC_CHECK(c4 == 32 && step >= 0 && step < 4 && ld % 8 == 0, "scale_to_index: c4 must be 32, step in 0..3");
+  ONEDC_CHECK(lut_lo >= 0 && lut_hi >= lut_lo && lut_hi - lut_lo <= 2048 && lut_hi <= 0x8000,
+              "scale_to_index: compact table range [lo, hi) must span at most 2048 positive bf16 patterns");
   ONEDC_CHECK(n_img <= 65535, "scale_to_index: batch too large");
   const long long hw = (long long)h * w;
   dim3 grid((unsigned)((hw + 127) / 128), n_img);
-  scale_to_index_kernel<32><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)scales, ld, lut, idx_out, step, h, w);
+  scale_to_index_kernel<32><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)scales, ld, lut, lut_lo, lut_hi, idx_out,
+                                                                     step, h, w);
   count_launch();
   ONEDC_CUDA(cudaGetLastError());
   return 0;

@@ -2,6 +2,8 @@
 // accesses, channel vectors mapped to threadIdx.x so that a warp reads 512 contiguous bytes of a pixel.
 #include "../../include/onedc_b200.h"
 #include "common.cuh"
+#include <stdlib.h>
+
 #include "ptx.cuh"
 
 namespace onedc {
@@ -28,6 +30,10 @@ __device__ __forceinline__ void load8(const void* base, int dtype, long long ele
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
   }
 }
+__device__ __forceinline__ void unpack8(const uint4& q, float* v) {
+  v[0] = bf16lo(q.x); v[1] = bf16hi(q.x); v[2] = bf16lo(q.y); v[3] = bf16hi(q.y);
+  v[4] = bf16lo(q.z); v[5] = bf16hi(q.z); v[6] = bf16lo(q.w); v[7] = bf16hi(q.w);
+}
 __device__ __forceinline__ void store8_bf16(void* base, long long elem_off, const float* v) {
   uint4 q;
   q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
@@ -42,13 +48,12 @@ struct GnSrc {
 };
 
 // Pass 1.  Block = 256 threads = VX channel-vectors (8 channels each) x PY pixel lanes over one chunk of pixels.
-// The block reduces its chunk to per-group (sum, sum of squares) in a fixed order and adds them as doubles to
-// acc[n][group][2] (fp64 atomics: the order-dependent error is ~1e-16 relative, invisible after the fp32 rounding
-// of mean / rstd).  The last block of an image (ticket counter) turns the totals into mean / rstd and zeroes the
-// accumulators and the counter again, so no memset launches are needed.
+// Every block reduces its chunk to per-group (sum, sum of squares) in a fixed order and writes them to
+// part[n][chunk*slabs + slab][group][2]; the last block of an image to finish (ticket counter) sums the block
+// partials in a fixed order in fp64 and writes mean / rstd: deterministic, no extra launch, no memset.
 template <int VX>
-__global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, long long hw, int chunk_px, int groups, float eps,
-                                                       double* acc, float* stats, unsigned int* counters) {
+__global__ void __launch_bounds__(256, 4) gn_stats_kernel(GnSrc s, long long hw, int chunk_px, int groups, float eps,
+                                                       float* part, float* stats, unsigned int* counters) {
   constexpr int PY = 256 / VX;
   __shared__ float red[PY][VX][16];
   __shared__ float chan[VX * 8][2];
@@ -63,32 +68,42 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, long long hw, in
   for (int j = 0; j < 8; j++) sum[j] = sq[j] = 0.f;
   if (active) {
     const bool first = v * 8 < s.c0;
-    const void* base = first ? s.x0 : s.x1;
+    const void* base_ptr = first ? s.x0 : s.x1;
     const long long ld = first ? s.ld0 : s.ld1;
     const int ch = first ? v * 8 : v * 8 - s.c0;
-    const long long p0 = (long long)chunk * chunk_px;
-    long long p1 = p0 + chunk_px;
-    if (p1 > hw) p1 = hw;
-    long long p = p0 + ty;
-    for (; p + 3 * PY < p1; p += 4 * PY) {          // 4 independent 16-byte loads in flight
-      float x[4][8];
+    // grid-stride over tiles of 8*PY pixels: at any moment the whole grid reads one compact address window
+    // (DRAM page locality); the assignment is fixed, so the summation order is too
+    (void)chunk_px;
+    constexpr int TILE = 8 * PY;
+    for (long long base = (long long)chunk * TILE; base < hw; base += (long long)gridDim.y * TILE) {
+      if (base + TILE <= hw && s.dtype == DT_BF16) {
+        // raw 16-byte vectors stay packed while in flight (4 registers each): 8 loads outstanding per thread at
+        // 4 resident blocks per SM = 128 KB in flight per SM
+        uint4 q[8];
+        const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(base_ptr);
 #pragma unroll
-      for (int u = 0; u < 4; u++) load8(base, s.dtype, ((long long)n * hw + p + u * PY) * ld + ch, x[u]);
+        for (int u = 0; u < 8; u++)
+          q[u] = __ldg(reinterpret_cast<const uint4*>(bp + ((long long)n * hw + base + ty + u * PY) * ld + ch));
 #pragma unroll
-      for (int u = 0; u < 4; u++)
+        for (int u = 0; u < 8; u++) {
+          float x[8];
+          unpack8(q[u], x);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-          sum[j] += x[u][j];
-          sq[j] += x[u][j] * x[u][j];
+          for (int j = 0; j < 8; j++) {
+            sum[j] += x[j];
+            sq[j] += x[j] * x[j];
+          }
         }
-    }
-    for (; p < p1; p += PY) {
-      float x[8];
-      load8(base, s.dtype, ((long long)n * hw + p) * ld + ch, x);
+      } else {
+        for (long long p = base + ty; p < hw; p += PY) {
+          float x[8];
+          load8(base_ptr, s.dtype, ((long long)n * hw + p) * ld + ch, x);
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        sum[j] += x[j];
-        sq[j] += x[j] * x[j];
+          for (int j = 0; j < 8; j++) {
+            sum[j] += x[j];
+            sq[j] += x[j] * x[j];
+          }
+        }
       }
     }
   }
@@ -112,51 +127,81 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc s, long long hw, in
     }
   }
   __syncthreads();
-  {
-    const int cpg = C / groups;
+  const int cpg = C / groups;
+  const int nblk = gridDim.x * gridDim.y;
+  const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+  if ((int)threadIdx.x < groups) {
+    // this block's contribution to every group (zero for groups outside its channel slab)
+    const int g = threadIdx.x;
     const int c0 = blockIdx.x * VX * 8;
     int c1 = c0 + VX * 8;
     if (c1 > C) c1 = C;
-    const int g_first = c0 / cpg, g_last = (c1 - 1) / cpg;
-    const int g = g_first + (int)threadIdx.x;
-    if (g <= g_last) {
-      int lo = g * cpg, hi = lo + cpg;
-      if (lo < c0) lo = c0;
-      if (hi > c1) hi = c1;
-      float a = 0.f, b = 0.f;
-      for (int c = lo; c < hi; c++) {
-        a += chan[c - c0][0];
-        b += chan[c - c0][1];
-      }
-      atomicAdd(&acc[((long long)n * groups + g) * 2], (double)a);
-      atomicAdd(&acc[((long long)n * groups + g) * 2 + 1], (double)b);
+    int lo = g * cpg, hi = lo + cpg;
+    if (lo < c0) lo = c0;
+    if (hi > c1) hi = c1;
+    float a = 0.f, b = 0.f;
+    for (int c = lo; c < hi; c++) {
+      a += chan[c - c0][0];
+      b += chan[c - c0][1];
     }
+    float2* dst = reinterpret_cast<float2*>(part) + ((long long)n * nblk + blk) * groups + g;
+    __stcg(dst, make_float2(a, b));
   }
   // ---- last block of this image finalises
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) ticket_s = atomicAdd(&counters[n], 1u);
   __syncthreads();
-  if (ticket_s != gridDim.x * gridDim.y - 1) return;
+  if (ticket_s != (unsigned)nblk - 1) return;
   __threadfence();
-  if ((int)threadIdx.x < groups) {
-    const int g = threadIdx.x;
-    double* pa = &acc[((long long)n * groups + g) * 2];
-    const double a = __ldcg(pa), b = __ldcg(pa + 1);
-    const double cnt = (double)hw * (C / groups);
-    const double mean = a / cnt;
-    double var = b / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    stats[((long long)n * groups + g) * 2] = (float)mean;
-    stats[((long long)n * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
-    pa[0] = 0.0;                              // self-cleaning for the next launch
-    pa[1] = 0.0;
+  // 256 threads = 8 sub-sums x 32 groups per pass; fixed assignment => deterministic
+  for (int gb = 0; gb < groups; gb += 32) {
+    const int g = gb + (threadIdx.x & 31), sub = threadIdx.x >> 5;
+    double a = 0.0, b = 0.0;
+    if (g < groups) {
+      const float2* src = reinterpret_cast<const float2*>(part) + (long long)n * nblk * groups + g;
+      int i = sub;
+      for (; i + 24 < nblk; i += 32) {
+        float2 f[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) f[u] = __ldcg(src + (long long)(i + 8 * u) * groups);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          a += (double)f[u].x;
+          b += (double)f[u].y;
+        }
+      }
+      for (; i < nblk; i += 8) {
+        const float2 f = __ldcg(src + (long long)i * groups);
+        a += (double)f.x;
+        b += (double)f.y;
+      }
+    }
+    __syncthreads();
+    double* dred = reinterpret_cast<double*>(&red[0][0][0]);      // 2 x 256 doubles = 4 KB of the 16 KB array
+    dred[threadIdx.x] = a;
+    dred[256 + threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.x < 32 && g < groups) {
+      double ta = 0.0, tb = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        ta += dred[k * 32 + threadIdx.x];
+        tb += dred[256 + k * 32 + threadIdx.x];
+      }
+      const double cnt = (double)hw * cpg;
+      const double mean = ta / cnt;
+      double var = tb / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stats[((long long)n * groups + g) * 2] = (float)mean;
+      stats[((long long)n * groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
   }
-  if (threadIdx.x == 0) counters[n] = 0;
+  if (threadIdx.x == 0) counters[n] = 0;       // self-cleaning
 }
 
 template <int VX>
-__global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, long long hw, int groups, const float* stats,
+__global__ void __launch_bounds__(256, 4) gn_apply_kernel(GnSrc s, long long hw, int groups, const float* stats,
                                                        const float* gamma, const float* beta, int silu, void* out,
                                                        long long out_ld, int px_per_block) {
   constexpr int PY = 256 / VX;
@@ -179,35 +224,40 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc s, long long hw, in
   const void* base = first ? s.x0 : s.x1;
   const long long ld = first ? s.ld0 : s.ld1;
   const int ch = first ? v * 8 : v * 8 - s.c0;
-  const long long p0 = (long long)blockIdx.y * px_per_block;
-  long long p1 = p0 + px_per_block;
-  if (p1 > hw) p1 = hw;
-  long long p = p0 + ty;
-  for (; p + 3 * PY < p1; p += 4 * PY) {
-    float x[4][8];
+  (void)px_per_block;
+  constexpr int TILE = 8 * PY;
+  for (long long tb = (long long)blockIdx.y * TILE; tb < hw; tb += (long long)gridDim.y * TILE) {
+    if (tb + TILE <= hw && s.dtype == DT_BF16) {
+      uint4 q[8];
+      const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(base);
 #pragma unroll
-    for (int u = 0; u < 4; u++) load8(base, s.dtype, ((long long)n * hw + p + u * PY) * ld + ch, x[u]);
+      for (int u = 0; u < 8; u++)
+        q[u] = __ldg(reinterpret_cast<const uint4*>(bp + ((long long)n * hw + tb + ty + u * PY) * ld + ch));
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < 8; u++) {
+        float x[8];
+        unpack8(q[u], x);
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        float y = x[u][j] * sc[j] + sh[j];
-        if (silu) y = __fdividef(y, 1.f + __expf(-y));
-        x[u][j] = y;
+        for (int j = 0; j < 8; j++) {
+          float y = x[j] * sc[j] + sh[j];
+          if (silu) y = __fdividef(y, 1.f + __expf(-y));
+          x[j] = y;
+        }
+        store8_bf16(out, ((long long)n * hw + tb + ty + u * PY) * out_ld + v * 8, x);
       }
-      store8_bf16(out, ((long long)n * hw + p + u * PY) * out_ld + v * 8, x[u]);
-    }
-  }
-  for (; p < p1; p += PY) {
-    float x[8];
-    load8(base, s.dtype, ((long long)n * hw + p) * ld + ch, x);
+    } else {
+      for (long long p = tb + ty; p < hw; p += PY) {
+        float x[8];
+        load8(base, s.dtype, ((long long)n * hw + p) * ld + ch, x);
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      float y = x[j] * sc[j] + sh[j];
-      if (silu) y = __fdividef(y, 1.f + __expf(-y));
-      x[j] = y;
+        for (int j = 0; j < 8; j++) {
+          float y = x[j] * sc[j] + sh[j];
+          if (silu) y = __fdividef(y, 1.f + __expf(-y));
+          x[j] = y;
+        }
+        store8_bf16(out, ((long long)n * hw + p) * out_ld + v * 8, x);
+      }
     }
-    store8_bf16(out, ((long long)n * hw + p) * out_ld + v * 8, x);
   }
 }
 
@@ -287,31 +337,56 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* s, long 
 
 using namespace onedc;
 
+static int gn_target_blocks() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ONEDC_GN_BLOCKS");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+static void gn_geometry(int C, long long hw, int* vx, int* slabs, int* px, int* chunks) {
+  const int nvec = C / 8;
+  *vx = nvec <= 16 ? 16 : 32;
+  *slabs = (nvec + *vx - 1) / *vx;
+  *px = gn_chunk_pixels(hw, *slabs, C);
+  if (gn_target_blocks() > 0) {
+    long long t = gn_target_blocks() / *slabs;
+    if (t < 1) t = 1;
+    long long p = (hw + t - 1) / t;
+    p = (p + 15) / 16 * 16;
+    *px = (int)(p < 16 ? 16 : p);
+  }
+  *chunks = (int)((hw + *px - 1) / *px);
+  const int tile = 8 * (256 / *vx);
+  const long long ntiles = (hw + tile - 1) / tile;
+  if (*chunks > ntiles) *chunks = (int)ntiles;
+  if (*chunks < 1) *chunks = 1;
+}
+
 extern "C" int64_t onedc_groupnorm_ws_floats(int32_t n_img, int64_t hw, int32_t c_total) {
-  (void)hw;
-  (void)c_total;
-  return (int64_t)n_img * 64 * 2;          // fp64 accumulators [n][groups<=64][2], counted in 4-byte units x2
+  int vx, slabs, px, chunks;
+  gn_geometry(c_total, hw, &vx, &slabs, &px, &chunks);
+  return (int64_t)n_img * slabs * chunks * 64 * 2;       // block partials [n][blocks][groups<=64][2]
 }
 
 extern "C" int onedc_groupnorm_stats(const void* x0, int32_t c0, int64_t ld0, const void* x1, int32_t c1, int64_t ld1,
                                      int32_t in_dtype, int32_t n_img, int64_t hw, int32_t groups, float eps,
-                                     double* acc, float* stats, uint32_t* counters, void* stream) {
+                                     float* partial, float* stats, uint32_t* counters, void* stream) {
   const int C = c0 + c1;
   ONEDC_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && C % groups == 0 && ld0 % 8 == 0 && ld1 % 8 == 0 && groups <= 64,
               "groupnorm: bad channels");
-  ONEDC_CHECK(counters != nullptr && acc != nullptr, "groupnorm: zero-initialised scratch is required");
+  ONEDC_CHECK(counters != nullptr && partial != nullptr, "groupnorm: scratch is required");
   GnSrc s{x0, x1, c0, c1, ld0, ld1, in_dtype};
-  const int nvec = C / 8;
-  const int vx = nvec <= 16 ? 16 : 32;
-  const int slabs = (nvec + vx - 1) / vx;
-  const int px = gn_chunk_pixels(hw, slabs, C);
-  const int chunks = (int)((hw + px - 1) / px);
+  int vx, slabs, px, chunks;
+  gn_geometry(C, hw, &vx, &slabs, &px, &chunks);
   ONEDC_CHECK(chunks <= 65535 && n_img <= 65535, "groupnorm: grid too large");
   dim3 grid(slabs, chunks, n_img);
   if (vx == 16)
-    gn_stats_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, px, groups, eps, acc, stats, counters);
+    gn_stats_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, px, groups, eps, partial, stats, counters);
   else
-    gn_stats_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, px, groups, eps, acc, stats, counters);
+    gn_stats_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, px, groups, eps, partial, stats, counters);
   count_launch();
   ONEDC_CUDA(cudaGetLastError());
   return 0;
@@ -325,8 +400,8 @@ extern "C" int onedc_groupnorm_apply(const void* x0, int32_t c0, int64_t ld0, co
   ONEDC_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && C % groups == 0 && out_ld % 8 == 0, "groupnorm: bad channels");
   GnSrc s{x0, x1, c0, c1, ld0, ld1, in_dtype};
   const int nvec = C / 8;
-  const int px = gn_chunk_pixels(hw, (nvec + (nvec <= 16 ? 15 : 31)) / (nvec <= 16 ? 16 : 32), C);
-  const int chunks = (int)((hw + px - 1) / px);
+  int vx_, slabs_, px, chunks;
+  gn_geometry(C, hw, &vx_, &slabs_, &px, &chunks);
   ONEDC_CHECK(chunks <= 65535 && n_img <= 65535, "groupnorm: grid too large");
   if (nvec <= 16) {
     dim3 grid((nvec + 15) / 16, chunks, n_img);

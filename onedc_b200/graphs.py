@@ -6,11 +6,14 @@ graphs (one graph for the device-resident leg) and replayed:
 
     G0 : FSQ codes -> hyper-synthesis -> prior fusion -> reduction -> index kernel(step 0) -> D2H indices
     Gk : H2D symbols(k-1) -> dequant(k-1) -> adaptor_k + prior net -> index kernel(k) -> D2H indices      k = 1..3
-    G4 : H2D symbols(3) -> dequant(3) -> semantic adaptor -> g_s -> UNet -> x0 -> VAE -> D2H image
+    Gs : (side stream, overlapping the loop and the host rANS) semantic adaptor -> sem_up half of g_s
+    G4 : H2D symbols(3) -> dequant(3) -> main half of g_s -> UNet -> x0 -> VAE -> D2H image
 
 Host<->device copies use fixed pinned buffers and are graph nodes; TMA descriptors are encoded at capture time against
 the (static) addresses of the graph's private memory pool.
 """
+import time
+
 import numpy as np
 import torch
 
@@ -37,6 +40,9 @@ class GraphedDecoder:
         self.sym_dev = torch.zeros((B, 32, self.h16, self.w16), dtype=torch.int16, device=dev)
         self.img_host = torch.zeros((B, 3, height, width), dtype=torch.float32, pin_memory=True)
         self.syms_res = [torch.zeros((B, 32, self.h16, self.w16), dtype=torch.int16, device=dev) for _ in range(4)]
+        self.side = torch.cuda.Stream(device=dev)
+        self.sem_done = torch.cuda.Event()
+        self.last_rans_ms = 0.0
         self.graphs = None
         self.g_res = None
         self.img_dev = None
@@ -59,17 +65,31 @@ class GraphedDecoder:
         ops.scale_to_index(self.sm[k][..., :128], c._lut(), k, self.idx_dev)
         self.idx_host.copy_(self.idx_dev.view(self.B, self.nsym), non_blocking=True)
 
+    def _seg_sem(self):
+        """Semantic branch (needs only z): semantic adaptor + the sem_up half of g_s.  Replayed on a side stream so
+        it fills the GPU while the host runs rANS; uses its own scratch lane."""
+        c = self.codec
+        ops.SCRATCH_LANE = 1
+        try:
+            codes = ops.fsq_codes(self.z_dev)
+            z_sem = ops.igemm(codes, c.hyper.feat_in, act=ops.ACT_LRELU, slope=0.01)
+            self.y_sem = c.semantic_adaptor(z_sem)
+            self.cat = c.dec.alloc_cat(self.B, self.h16, self.w16, self.dev)
+            c.dec.sem_path(self.y_sem, self.cat)
+        finally:
+            ops.SCRATCH_LANE = 0
+
     def _seg4(self):
         c = self.codec
         self.sym_dev.view(self.B, self.nsym).copy_(self.sym_host, non_blocking=True)
         ops.dequant_accum(self.sym_dev, self.sm[3][..., 128:], self.params[..., :128], 3)
-        y_sem = c.semantic_adaptor(self.z_sem)
-        x_hat = c.dec(self.params[..., :128], y_sem)
-        self.img_dev = self.model.generate(x_hat, y_sem)
+        x_hat = c.dec.main_path(self.params[..., :128], self.cat)
+        self.img_dev = self.model.generate(x_hat, self.y_sem)
         self.img_host.copy_(self.img_dev, non_blocking=True)
 
     def _segments(self):
-        return [self._seg0, lambda: self._segk(1), lambda: self._segk(2), lambda: self._segk(3), self._seg4]
+        return [self._seg0, lambda: self._segk(1), lambda: self._segk(2), lambda: self._segk(3), self._seg_sem,
+                self._seg4]
 
     def capture(self):
         """Warm up eagerly once (function attributes, allocator), then capture the five segments into one pool."""
@@ -86,10 +106,11 @@ class GraphedDecoder:
         pool = torch.cuda.graph_pool_handle()
         self.graphs = []
         n0 = lib.launch_count()
-        with torch.no_grad():
-            for seg in self._segments():
+        sem_pool = torch.cuda.graph_pool_handle()     # the semantic graph runs CONCURRENTLY with G1..G3: its memory
+        with torch.no_grad():                          # must never alias their (recycled) temporaries
+            for i, seg in enumerate(self._segments()):
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool):
+                with torch.cuda.graph(g, pool=sem_pool if i == 4 else pool):
                     seg()
                 self.graphs.append(g)
         self.launches = lib.launch_count() - n0
@@ -124,16 +145,26 @@ class GraphedDecoder:
         decoders = [StreamDecoder(c.entropy_coder, d["bit_stream_y"], c.gaussian_encoder.cdf_group_index) for d in hdrs]
         stream = torch.cuda.current_stream()
         self.z_dev.copy_(self.z_host, non_blocking=True)
+        # semantic branch on the side stream: overlaps the prior loop and the host rANS calls
+        self.side.wait_stream(stream)
+        with torch.cuda.stream(self.side):
+            self.graphs[4].replay()
+            self.sem_done.record(self.side)
         ip, sp, n = self.idx_host.data_ptr(), self.sym_host.data_ptr(), self.nsym
+        t_rans = 0.0
         for k in range(4):
             self.graphs[k].replay()
             stream.synchronize()
+            t0 = time.perf_counter()
             if self.B == 1:
                 decoders[0].decode_into(ip, n, sp)
             else:
                 list(c._pool.map(lambda i: decoders[i].decode_into(ip + 2 * i * n, n, sp + 2 * i * n), range(self.B)))
-        self.graphs[4].replay()
+            t_rans += time.perf_counter() - t0
+        stream.wait_event(self.sem_done)
+        self.graphs[5].replay()
         stream.synchronize()
+        self.last_rans_ms = t_rans * 1e3
         return self.img_host, hdrs
 
     def set_resident_inputs(self, z_idx, syms):

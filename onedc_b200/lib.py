@@ -53,7 +53,7 @@ PROTOTYPES = {
     "onedc_window_partition": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "onedc_window_merge": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "onedc_x0_prepare": (C.c_int, [_vp, _vp, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _i64, _vp]),
-    "onedc_scale_to_index": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "onedc_scale_to_index": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "onedc_build_indexes": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i64, _vp]),
     "onedc_dequant_accum": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "onedc_quantize_residual": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),

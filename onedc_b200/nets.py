@@ -184,9 +184,17 @@ class LatentSynthesisNet:
                     RBU(sd, "dec.sem_up.4", 256, 256, dev)]
         self.conv_out = DCB4(sd, "dec.conv_out", 512, 320, dev)
 
-    def __call__(self, y_hat, y_sem):
-        n, h16, w16, _ = y_hat.shape
-        cat = torch.empty((n, 2 * h16, 2 * w16, 512), device=y_hat.device, dtype=torch.bfloat16)
+    def alloc_cat(self, n, h16, w16, device):
+        return torch.empty((n, 2 * h16, 2 * w16, 512), device=device, dtype=torch.bfloat16)
+
+    def sem_path(self, y_sem, cat):
+        """semantic branch: independent of y, so it can run while the host decodes the y stream"""
+        s = y_sem
+        for m in self.sem[:-1]:
+            s = m(s)
+        self.sem[-1](s, out=cat[..., 256:])
+
+    def main_path(self, y_hat, cat):
         t = y_hat
         for m in self.tc + self.res16:
             t = m(t)
@@ -195,11 +203,13 @@ class LatentSynthesisNet:
         t = self.res8[0](t)
         t = self.res8[1](t)
         self.res8[2](t, out=cat[..., :256])
-        s = y_sem
-        for m in self.sem[:-1]:
-            s = m(s)
-        self.sem[-1](s, out=cat[..., 256:])
         return self.conv_out(cat)
+
+    def __call__(self, y_hat, y_sem):
+        n, h16, w16, _ = y_hat.shape
+        cat = self.alloc_cat(n, h16, w16, y_hat.device)
+        self.sem_path(y_sem, cat)
+        return self.main_path(y_hat, cat)
 
 
 # ============================================================================ UNet

@@ -142,6 +142,9 @@ def pixshuf_permute(w, b):
     return w[idx], (None if b is None else b[idx])
 
 
+# scratch buffers are per (device, lane): kernels of one stream are ordered, but two streams that run
+# concurrently (the semantic branch overlapping the prior loop) must not share split-K / GroupNorm scratch
+SCRATCH_LANE = 0
 _splitk_scratch = {}
 SPLITK = os.environ.get("ONEDC_SPLITK", "1") == "1"
 
@@ -149,7 +152,7 @@ SPLITK = os.environ.get("ONEDC_SPLITK", "1") == "1"
 def _splitk_buffers(device):
     """fp32 partial-tile workspace (148 tiles x 128 x 256) + self-cleaning arrival counters, shared by all launches
     of a stream (launches are stream-ordered, so one scratch is enough)."""
-    key = str(device)
+    key = (str(device), SCRATCH_LANE)
     if key not in _splitk_scratch:
         _splitk_scratch[key] = (torch.empty(160 * 128 * 256, device=device, dtype=torch.float32),
                                 torch.zeros(256, device=device, dtype=torch.int32))
@@ -264,10 +267,10 @@ _gn_scratch = {}
 
 
 def _gn_buffers(device):
-    """Shared, self-cleaning scratch of the GroupNorm statistics pass (fp64 accumulators + block tickets)."""
-    key = str(device)
+    """Shared scratch of the GroupNorm statistics pass (per-block partial sums + self-cleaning block tickets)."""
+    key = (str(device), SCRATCH_LANE)
     if key not in _gn_scratch:
-        _gn_scratch[key] = (torch.zeros(256 * 64 * 2, device=device, dtype=torch.float64),
+        _gn_scratch[key] = (torch.empty(1 << 20, device=device, dtype=torch.float32),     # block partial sums
                             torch.zeros(256, device=device, dtype=torch.int32))
     return _gn_scratch[key]
 
@@ -287,6 +290,7 @@ class GroupNorm:
         hw, ct = h * w, c0 + c1
         assert n <= 256
         acc, counters = _gn_buffers(x.device)
+        assert lib.onedc_groupnorm_ws_floats(n, hw, ct) <= acc.numel()
         stats = torch.empty((n, self.groups, 2), device=x.device, dtype=torch.float32)
         L.check(lib.onedc_groupnorm_stats(p0, c0, s0, p1, c1, s1, _dt(x), n, hw, self.groups, self.eps,
                                           acc.data_ptr(), stats.data_ptr(), counters.data_ptr(), _stream()),
@@ -372,12 +376,30 @@ def x0_prepare(reduced, eps, sqrt_alpha, sqrt_1m_alpha, inv_scaling, pq_w, pq_b,
     return out, x0
 
 
+_lut_range = {}
+
+
+def lut_range(lut):
+    """[lo, hi): positive bf16 bit patterns whose index is neither 0 nor 255 (derived from the table itself)."""
+    key = lut.data_ptr()
+    if key not in _lut_range:
+        pos = lut[:0x8000].cpu()
+        nz = torch.nonzero(pos > 0)
+        lo = int(nz[0]) if len(nz) else 0x8000
+        full = torch.nonzero(pos == 255)
+        hi = int(full[0]) if len(full) else 0x8000
+        assert bool((pos[:lo] == 0).all()) and bool((pos[hi:0x7F81] == 255).all()) and hi - lo <= 2048
+        _lut_range[key] = (lo, hi)
+    return _lut_range[key]
+
+
 def scale_to_index(scales, lut, step, idx_out=None):
     p, n, h, w, c, s = _nhwc(scales)
     assert c == 128
     if idx_out is None:
         idx_out = torch.empty((n, 32, h, w), device=scales.device, dtype=torch.int16)
-    L.check(L.load().onedc_scale_to_index(p, s, lut.data_ptr(), idx_out.data_ptr(), step, n, h, w, 32, _stream()),
+    lo, hi = lut_range(lut)
+    L.check(L.load().onedc_scale_to_index(p, s, lut.data_ptr(), lo, hi, idx_out.data_ptr(), step, n, h, w, 32, _stream()),
             "scale_to_index")
     return idx_out
 

@@ -40,4 +40,13 @@ total = sum(tot.values())
 print(f"total kernel time per step {total / 3 / 1e3:.3f} ms")
 for k, v in rows[:16]:
     print(f"{k[:60]:60s} n/step={cnt[k] // 3:4d}  {v / 3 / 1e3:8.3f} ms  {100 * v / total:5.1f}%")
+trace = a.out.replace(".json", "_trace.json")
+prof.export_chrome_trace(trace)
+ev = [e for e in json.load(open(trace))["traceEvents"] if e.get("cat") == "kernel"]
+ev.sort(key=lambda e: e["ts"])
+per = len(ev) // 3
+rows2 = [{"i": i, "name": e["name"].split("(")[0][:48], "us": e["dur"], "grid": e["args"].get("grid"), "block": e["args"].get("block")}
+         for i, e in enumerate(ev[2 * per:])]
+json.dump(rows2, open(a.out.replace(".json", "_launches.json"), "w"))
+os.remove(trace)
 json.dump({k: {"ms_per_step": v / 3 / 1e3, "launches_per_step": cnt[k] // 3} for k, v in rows}, open(a.out, "w"), indent=1)
