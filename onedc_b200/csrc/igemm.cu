@@ -460,35 +460,52 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const int r0 = 128 * split / p.splits, r1 = 128 * (split + 1) / p.splits;
+        // B1: all 256 threads sum this CTA's row slice over the splits (fixed order) with coalesced 16-byte loads,
+        //     several splits in flight per position, into the (now idle) operand ring in shared memory
+        float* red = reinterpret_cast<float*>(smem);
+        const int slice_f4 = (r1 - r0) * (p.BN >> 2);
+        const size_t sstride4 = (size_t)128 * (p.BN >> 2);
+        const float4* wsl = reinterpret_cast<const float4*>(p.ws + ((size_t)tile * p.splits * 128 + r0) * p.BN);
+        for (int e = etid; e < slice_f4; e += 256) {
+          float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          int s2 = 0;
+          for (; s2 + 4 <= p.splits; s2 += 4) {
+            float4 f[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) f[u] = __ldcg(wsl + (size_t)(s2 + u) * sstride4 + e);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              acc4.x += f[u].x; acc4.y += f[u].y; acc4.z += f[u].z; acc4.w += f[u].w;
+            }
+          }
+          for (; s2 < p.splits; s2++) {
+            const float4 f = __ldcg(wsl + (size_t)s2 * sstride4 + e);
+            acc4.x += f.x; acc4.y += f.y; acc4.z += f.z; acc4.w += f.w;
+          }
+          reinterpret_cast<float4*>(red)[e] = acc4;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // B2: (row, 32-column chunk) tasks run the real epilogue from shared memory
         const int nch = out_cols_tile >> 5;
         const int tasks = (r1 - r0) * nch;
-        const size_t sstride = (size_t)128 * p.BN;
         for (int task = etid; task < tasks; task += 256) {
-          const int rr = r0 + task / nch, c = (task % nch) << 5;
+          const int rl = task / nch, c = (task % nch) << 5;
+          const int rr = r0 + rl;
           const int yy = t.y0 + rr / p.TW, xx = t.x0 + rr % p.TW;
           const bool vld = (rr < p.TH * p.TW) && (yy < p.H) && (xx < p.W);
-          const float* wbase = p.ws + ((size_t)tile * p.splits * 128 + rr) * p.BN;
           float a[32], b[32];
+          const float4* ra = reinterpret_cast<const float4*>(red + (size_t)rl * p.BN + c);
 #pragma unroll
-          for (int i = 0; i < 32; i++) a[i] = 0.f;
-          if (pair) {
-#pragma unroll
-            for (int i = 0; i < 32; i++) b[i] = 0.f;
+          for (int i = 0; i < 8; i++) {
+            const float4 f = ra[i];
+            a[4 * i] = f.x; a[4 * i + 1] = f.y; a[4 * i + 2] = f.z; a[4 * i + 3] = f.w;
           }
-          for (int s2 = 0; s2 < p.splits; s2++) {
-            const float4* s4 = reinterpret_cast<const float4*>(wbase + s2 * sstride + c);
+          if (pair) {
+            const float4* rb = reinterpret_cast<const float4*>(red + (size_t)rl * p.BN + half + c);
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-              const float4 f = __ldcg(s4 + i);
-              a[4 * i] += f.x; a[4 * i + 1] += f.y; a[4 * i + 2] += f.z; a[4 * i + 3] += f.w;
-            }
-            if (pair) {
-              const float4* t4 = reinterpret_cast<const float4*>(wbase + s2 * sstride + half + c);
-#pragma unroll
-              for (int i = 0; i < 8; i++) {
-                const float4 f = __ldcg(t4 + i);
-                b[4 * i] += f.x; b[4 * i + 1] += f.y; b[4 * i + 2] += f.z; b[4 * i + 3] += f.w;
-              }
+              const float4 f = rb[i];
+              b[4 * i] = f.x; b[4 * i + 1] = f.y; b[4 * i + 2] = f.z; b[4 * i + 3] = f.w;
             }
           }
           const long long pix2 = ((long long)t.img * p.H + yy) * p.W + xx;
@@ -687,10 +704,11 @@ int make_tensor_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* d
 }
 
 static int pick_bn(int cout, bool pair) {
-  const int step = pair ? 32 : 16;
-  if (cout <= 256) return ((cout + step - 1) / step) * step;
+  (void)pair;
+  // the vector epilogue works on 32-column chunks: prefer N tiles that are multiples of 32
+  if (cout <= 256) return cout % 32 == 0 ? cout : ((cout + 15) / 16) * 16;
   int best = 256, best_waste = 1 << 30;
-  for (int bn = 256; bn >= 96; bn -= step) {
+  for (int bn = 256; bn >= 96; bn -= 32) {
     int nt = (cout + bn - 1) / bn;
     int waste = nt * bn - cout;
     if (waste < best_waste) {
@@ -750,6 +768,23 @@ static int igemm_launch(const onedc_igemm_desc* d, cudaStream_t stream) {
   p.BN = d->bn > 0 ? d->bn : pick_bn(d->cout, pair);
   ONEDC_CHECK(p.BN >= 16 && p.BN <= 256 && p.BN % (pair ? 32 : 16) == 0, "igemm: bad BN %d", p.BN);
   p.n_tiles = (d->cout + p.BN - 1) / p.BN;
+  if (d->bn <= 0 && !pair && d->impl == 0) {
+    // few tiles and a short K loop (split-K will not apply): halve the N tile while that still fits one wave,
+    // so twice as many SMs share the MMA work (A tiles are re-read from L2, which is cheap at these sizes)
+    int th0, tw0;
+    const int Ho = d->stride == 2 ? d->h_in / 2 : d->h_in, Wo = d->stride == 2 ? d->w_in / 2 : d->w_in;
+    pick_tile(Ho, Wo, &th0, &tw0);
+    const int mt = d->n_img * ((Ho + th0 - 1) / th0) * ((Wo + tw0 - 1) / tw0);
+    const int taps0 = d->ntaps > 0 ? d->ntaps : d->ksize * d->ksize;
+    const int kit = taps0 * ((d->a_c[0] + 63) / 64 + (d->a_c[1] + 63) / 64);
+    const bool will_split = d->splitk_ws != nullptr && mt * p.n_tiles * 2 <= sm_count() && kit >= 32 &&
+                            sm_count() / (mt * p.n_tiles) >= 4;
+    while (!will_split && p.BN % 64 == 0 && p.BN >= 128 && d->cout % (p.BN / 2) == 0 &&
+           mt * ((d->cout + p.BN / 2 - 1) / (p.BN / 2)) <= sm_count()) {
+      p.BN /= 2;
+      p.n_tiles = (d->cout + p.BN - 1) / p.BN;
+    }
+  }
   if (pair) ONEDC_CHECK(d->cout % p.BN == 0, "igemm: pair epilogues need cout %% BN == 0 (cout %d BN %d)", d->cout, p.BN);
   pick_tile(p.H, p.W, &p.TH, &p.TW);
   p.tiles_y = (p.H + p.TH - 1) / p.TH;

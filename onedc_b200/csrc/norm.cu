@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(256, 4) gn_stats_kernel(GnSrc s, long long hw,
           }
         }
       } else {
-        for (long long p = base + ty; p < hw; p += PY) {
+        const long long pend = base + TILE < hw ? base + TILE : hw;
+        for (long long p = base + ty; p < pend; p += PY) {
           float x[8];
           load8(base_ptr, s.dtype, ((long long)n * hw + p) * ld + ch, x);
 #pragma unroll
@@ -246,7 +247,8 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(GnSrc s, long long hw,
         store8_bf16(out, ((long long)n * hw + tb + ty + u * PY) * out_ld + v * 8, x);
       }
     } else {
-      for (long long p = tb + ty; p < hw; p += PY) {
+      const long long pend = tb + TILE < hw ? tb + TILE : hw;
+      for (long long p = tb + ty; p < pend; p += PY) {
         float x[8];
         load8(base, s.dtype, ((long long)n * hw + p) * ld + ch, x);
 #pragma unroll
