@@ -123,11 +123,12 @@ int onedc_attention(const void* q, int64_t q_ld, const void* k, const void* v, i
 /* GroupNorm over the channel concatenation of up to two NHWC sources. partial: fp32 scratch of
  * onedc_groupnorm_ws_floats() floats (per-block group sums); counters: n_img uint32, zero on entry and zero again
  * on exit (the last block of an image merges the block sums in a fixed order); stats: fp32 [n_img][groups][2]
- * (mean, rstd). */
+ * (mean, rstd).  valid_px (device int32[n_img] or NULL): number of real pixels per image when the rest is zero
+ * padding (edge windows of the VAE attention): the statistics then cover the real pixels only. */
 int64_t onedc_groupnorm_ws_floats(int32_t n_img, int64_t hw, int32_t c_total);
 int onedc_groupnorm_stats(const void* x0, int32_t c0, int64_t ld0, const void* x1, int32_t c1, int64_t ld1,
                           int32_t in_dtype, int32_t n_img, int64_t hw, int32_t groups, float eps, float* partial,
-                          float* stats, uint32_t* counters, void* stream);
+                          float* stats, uint32_t* counters, const int32_t* valid_px, void* stream);
 int onedc_groupnorm_apply(const void* x0, int32_t c0, int64_t ld0, const void* x1, int32_t c1, int64_t ld1,
                           int32_t in_dtype, int32_t n_img, int64_t hw, int32_t groups, const float* stats,
                           const float* gamma, const float* beta, int32_t silu, void* out, int64_t out_ld,

@@ -53,7 +53,8 @@ struct GnSrc {
 // partials in a fixed order in fp64 and writes mean / rstd: deterministic, no extra launch, no memset.
 template <int VX>
 __global__ void __launch_bounds__(256, 4) gn_stats_kernel(GnSrc s, long long hw, int chunk_px, int groups, float eps,
-                                                       float* part, float* stats, unsigned int* counters) {
+                                                       float* part, float* stats, unsigned int* counters,
+                                                       const int* valid_px) {
   constexpr int PY = 256 / VX;
   __shared__ float red[PY][VX][16];
   __shared__ float chan[VX * 8][2];
@@ -190,7 +191,8 @@ __global__ void __launch_bounds__(256, 4) gn_stats_kernel(GnSrc s, long long hw,
         ta += dred[k * 32 + threadIdx.x];
         tb += dred[256 + k * 32 + threadIdx.x];
       }
-      const double cnt = (double)hw * cpg;
+      // zero-padded pixels (edge attention windows) add nothing to the sums: only the count changes
+      const double cnt = (double)(valid_px != nullptr ? (long long)valid_px[n] : hw) * cpg;
       const double mean = ta / cnt;
       double var = tb / cnt - mean * mean;
       if (var < 0.0) var = 0.0;
@@ -375,7 +377,7 @@ extern "C" int64_t onedc_groupnorm_ws_floats(int32_t n_img, int64_t hw, int32_t 
 
 extern "C" int onedc_groupnorm_stats(const void* x0, int32_t c0, int64_t ld0, const void* x1, int32_t c1, int64_t ld1,
                                      int32_t in_dtype, int32_t n_img, int64_t hw, int32_t groups, float eps,
-                                     float* partial, float* stats, uint32_t* counters, void* stream) {
+                                     float* partial, float* stats, uint32_t* counters, const int32_t* valid_px, void* stream) {
   const int C = c0 + c1;
   ONEDC_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && C % groups == 0 && ld0 % 8 == 0 && ld1 % 8 == 0 && groups <= 64,
               "groupnorm: bad channels");
@@ -386,9 +388,9 @@ extern "C" int onedc_groupnorm_stats(const void* x0, int32_t c0, int64_t ld0, co
   ONEDC_CHECK(chunks <= 65535 && n_img <= 65535, "groupnorm: grid too large");
   dim3 grid(slabs, chunks, n_img);
   if (vx == 16)
-    gn_stats_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, px, groups, eps, partial, stats, counters);
+    gn_stats_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, px, groups, eps, partial, stats, counters, valid_px);
   else
-    gn_stats_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, px, groups, eps, partial, stats, counters);
+    gn_stats_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, px, groups, eps, partial, stats, counters, valid_px);
   count_launch();
   ONEDC_CUDA(cudaGetLastError());
   return 0;

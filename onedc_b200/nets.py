@@ -402,6 +402,7 @@ class VAEWindowAttention:
 
     def __init__(self, sd, p, c, win, dev):
         self.c, self.win = c, win
+        self._valid = {}
         self.norm = GroupNorm(sd[p + ".group_norm.weight"], sd[p + ".group_norm.bias"], 1e-6, device=dev)
         wq, bq = _wb(sd, p + ".to_q")
         wk, bk = _wb(sd, p + ".to_k")
@@ -419,11 +420,15 @@ class VAEWindowAttention:
         xw = ops.window_partition(x, win)                                  # [nwin, T, c]
         valid = None
         if h % win or w % win:
-            vh = torch.tensor([min(win, h - i * win) for i in range(nwy)])
-            vw = torch.tensor([min(win, w - j * win) for j in range(nwx)])
-            valid = (vh[:, None] * vw[None, :]).reshape(-1).repeat(n).to(device=x.device, dtype=torch.int32)
-            assert False, "edge windows: per-window GroupNorm over the valid tokens is not implemented yet"
-        hn = self.norm(xw.view(nwin, 1, T, c), silu=False)
+            # edge windows hold fewer tokens: the partition zero-pads them to T rows; GroupNorm counts and the
+            # softmax key range use the real token count of each window
+            key = (n, h, w, str(x.device))
+            if key not in self._valid:
+                vh = torch.tensor([min(win, h - i * win) for i in range(nwy)])
+                vw = torch.tensor([min(win, w - j * win) for j in range(nwx)])
+                self._valid[key] = (vh[:, None] * vw[None, :]).reshape(-1).repeat(n).to(device=x.device, dtype=torch.int32)
+            valid = self._valid[key]
+        hn = self.norm(xw.view(nwin, 1, T, c), silu=False, valid=valid)
         qk = igemm(hn, self.qk).view(nwin, T, 2 * c)
         vT = torch.empty((nwin, c, T), device=x.device, dtype=torch.bfloat16)
         igemm(hn, self.v, store=ST_TRANSPOSED, out=vT)

@@ -281,7 +281,8 @@ class GroupNorm:
         self.beta = beta.detach().float().contiguous().to(device)
         self.eps, self.groups = eps, groups
 
-    def __call__(self, x, x2=None, silu=True, out=None):
+    def __call__(self, x, x2=None, silu=True, out=None, valid=None):
+        """valid: optional int32 [n] device tensor = real pixels per image (the others are zero padding)."""
         lib = L.load()
         p0, n, h, w, c0, s0 = _nhwc(x)
         p1, c1, s1 = 0, 0, 0
@@ -293,8 +294,8 @@ class GroupNorm:
         assert lib.onedc_groupnorm_ws_floats(n, hw, ct) <= acc.numel()
         stats = torch.empty((n, self.groups, 2), device=x.device, dtype=torch.float32)
         L.check(lib.onedc_groupnorm_stats(p0, c0, s0, p1, c1, s1, _dt(x), n, hw, self.groups, self.eps,
-                                          acc.data_ptr(), stats.data_ptr(), counters.data_ptr(), _stream()),
-                "groupnorm_stats")
+                                          acc.data_ptr(), stats.data_ptr(), counters.data_ptr(),
+                                          0 if valid is None else valid.data_ptr(), _stream()), "groupnorm_stats")
         if out is None:
             out = torch.empty((n, h, w, ct) if x.dim() == 4 else (n, hw, ct), device=x.device, dtype=torch.bfloat16)
         po, _, _, _, _, so = _nhwc(out)

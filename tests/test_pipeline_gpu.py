@@ -160,3 +160,20 @@ def test_graph_replay_matches_eager(bundle):
     assert torch.equal(eager, g1), "graph replay differs from eager"
     host = model.last_host_images
     assert torch.equal(host[:, :, :H, :W], g1.cpu())
+
+
+@pytest.mark.parametrize("hh,ww", [(192, 320), (100, 70)])
+def test_sizes_with_edge_windows_and_padding(bundle, hh, ww):
+    """Sizes whose latent is not a multiple of the 16-token VAE attention window (edge windows are smaller,
+    autoencoders_patch_attn.py:22-28) and sizes that need right/bottom padding to a multiple of 64."""
+    model, oracle = bundle["model"], bundle["oracle"]
+    stream, _ = model.codec_model.compress_synthetic(hh, ww, seed=4321)
+    st = {}
+    img = model.decode(stream=stream, stages=st)
+    assert img.shape == (1, 3, hh, ww)
+    ref = oracle.generate(st["x_hat"], st["y_sem"]).cpu()[:, :, :hh, :ww]
+    p = _psnr01(img.cpu(), ref)
+    print(f"{hh}x{ww}: PSNR vs oracle generator {p:.2f} dB")
+    assert p >= 45.0
+    g = model.decode(stream=stream)                       # graph route, same bits
+    assert torch.equal(g, img)
