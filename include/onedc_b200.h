@@ -109,9 +109,16 @@ typedef struct {
   int32_t ntaps;
   int32_t tap_dy[9], tap_dx[9];
   int32_t quad;
+  /* optional fused GroupNorm statistics of the stored output: gn_acc = device fp64 [n_img][gn_groups][2] (sum, sum
+   * of squares per group of cout/gn_groups consecutive channels), zero-initialised by the caller, accumulated with
+   * atomics.  Only done when the whole launch runs on the vector-store path without split-K and the group size is
+   * 4, 8, 16 or 32 channels; gn_fused_out (written by the call) says whether it was. */
+  void* gn_acc;
+  int32_t gn_groups;
+  int32_t gn_fused_out;
 } onedc_igemm_desc;
 
-int onedc_igemm(const onedc_igemm_desc* d, void* stream);
+int onedc_igemm(onedc_igemm_desc* d, void* stream);
 
 /* ---- flash attention on tcgen05 (multi-head, head_dim 40/80/160) -------------------------- */
 /* q: [batch, sq, q_ld] bf16 (head h at columns h*d), k/v: [batch, skv, kv_ld], out: [batch, sq, o_ld] */
@@ -129,10 +136,13 @@ int64_t onedc_groupnorm_ws_floats(int32_t n_img, int64_t hw, int32_t c_total);
 int onedc_groupnorm_stats(const void* x0, int32_t c0, int64_t ld0, const void* x1, int32_t c1, int64_t ld1,
                           int32_t in_dtype, int32_t n_img, int64_t hw, int32_t groups, float eps, float* partial,
                           float* stats, uint32_t* counters, const int32_t* valid_px, void* stream);
+/* statistics come either from `stats` (onedc_groupnorm_stats) or, when acc0 != NULL (single source only), from the
+ * per-group fp64 (sum, sum of squares) accumulators [n_img][groups][2] that onedc_igemm fused into the producer's
+ * epilogue; acc1 is reserved */
 int onedc_groupnorm_apply(const void* x0, int32_t c0, int64_t ld0, const void* x1, int32_t c1, int64_t ld1,
                           int32_t in_dtype, int32_t n_img, int64_t hw, int32_t groups, const float* stats,
-                          const float* gamma, const float* beta, int32_t silu, void* out, int64_t out_ld,
-                          void* stream);
+                          const double* acc0, const double* acc1, float eps, const float* gamma, const float* beta,
+                          int32_t silu, void* out, int64_t out_ld, void* stream);
 int onedc_layernorm(const void* x, int64_t ld, int64_t rows, int32_t c, const float* gamma, const float* beta,
                     float eps, void* out, int64_t out_ld, void* stream);
 /* scores fp32 [rows, ld] -> bf16 probabilities [rows, out_ld]; columns >= valid are written as 0 */

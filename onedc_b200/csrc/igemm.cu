@@ -57,6 +57,8 @@ struct IgemmParams {
   int ncols_out;          // cout (plain) or cout/2 (pair modes)
   int vec_ok;
   // split-K (small-M layers): fp32 partial tiles + per-tile arrival counters
+  double* gn_acc;         // optional per-GROUP (sum, sum of squares) of the stored outputs, [img][gn_groups][2]
+  int gn_ng, gn_groups;   // groups per 32-column chunk (8/4/2/1, i.e. 4/8/16/32 channels per group), groups per image
   int splits;
   float* ws;
   int* counters;
@@ -185,6 +187,54 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile)
   t.y0 = ty * p.TH;
   t.x0 = (r - ty * p.tiles_x) * p.TW;
   return t;
+}
+
+// Reduces NG (= 8, 4, 2 or 1) per-thread values over the 32 lanes of a warp: halving butterfly while more than one
+// value is left, plain xor all-reduce afterwards.  On return every lane holds in v[0] the warp total of the value
+// with index (lane >> log2(32 / NG)), i.e. 32/NG consecutive lanes share one value.
+template <int NG>
+__device__ __forceinline__ float warp_group_sum(float* v, int lane) {
+  int n = NG;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    if (n > 1) {
+      const bool upper = (lane & off) != 0;
+      const int h = n >> 1;
+#pragma unroll
+      for (int i = 0; i < NG / 2; i++) {
+        if (i < h) {
+          const float mine = upper ? v[i + h] : v[i];
+          const float send = upper ? v[i] : v[i + h];
+          v[i] = mine + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      n = h;
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+    }
+  }
+  return v[0];
+}
+
+// per-thread sums of `cpg` consecutive values (cpg = 32 / NG) of a[32] and of their squares, then warp reduction
+template <int NG>
+__device__ __forceinline__ void chunk_group_stats(const float* a, bool valid, int lane, float* s_out, float* q_out) {
+  constexpr int CPG = 32 / NG;
+  float gs[NG], gq[NG];
+#pragma unroll
+  for (int j = 0; j < NG; j++) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPG; i++) {
+      const float x = valid ? a[j * CPG + i] : 0.f;
+      s1 += x;
+      s2 += x * x;
+    }
+    gs[j] = s1;
+    gq[j] = s2;
+  }
+  *s_out = warp_group_sum<NG>(gs, lane);
+  *q_out = warp_group_sum<NG>(gq, lane);
 }
 
 // Finishes 32 output columns of one pixel: v[] already holds accumulator (+ nothing else) values.
@@ -414,6 +464,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     const bool pair = p.epi_mode != EPI_PLAIN;
     const int half = p.BN >> 1;
     const int out_cols_tile = pair ? half : p.BN;      // output columns produced per tile
+    float csum[4] = {0.f, 0.f, 0.f, 0.f}, csq[4] = {0.f, 0.f, 0.f, 0.f};   // fused GroupNorm statistics
+    int st_img = -1, st_nt = -1;
     int it = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, it++) {
       const int tile = item / nsplit, split = item - tile * nsplit;
@@ -526,6 +578,24 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         continue;
       }
       if (fast) {
+        const bool want_stats = !pair && p.gn_acc != nullptr;
+        if (want_stats && (t.img != st_img || t.n_tile != st_nt)) {
+          if (st_img >= 0) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const int cl = member * 32 + k * 64;
+              if (cl < out_cols_tile && (lane & (32 / p.gn_ng - 1)) == 0) {
+                const int g = ((st_nt * out_cols_tile + cl) >> 5) * p.gn_ng + lane / (32 / p.gn_ng);
+                double* dst = p.gn_acc + ((size_t)st_img * p.gn_groups + g) * 2;
+                atomicAdd(dst, (double)csum[k]);
+                atomicAdd(dst + 1, (double)csq[k]);
+              }
+              csum[k] = csq[k] = 0.f;
+            }
+          }
+          st_img = t.img;
+          st_nt = t.n_tile;
+        }
         for (int c = member * 32; c < out_cols_tile; c += 64) {
           float a[32], b[32];
           {
@@ -547,6 +617,22 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             epi_finish32<true>(p, a, b, &bias_s[acc][c], &bias_s[acc][half + c], valid, t.img, y, x, pix, o0 + c);
           else
             epi_finish32<false>(p, a, a, &bias_s[acc][c], &bias_s[acc][c], valid, t.img, y, x, pix, o0 + c);
+          if (want_stats) {
+            // GroupNorm statistics of what was just stored: per-group sums over this warp's 32 rows, kept in
+            // registers across the CTA's tiles, flushed with one fp64 atomic per group when the tile column changes
+            float s1, s2;
+            if (p.gn_ng == 8) chunk_group_stats<8>(a, valid, lane, &s1, &s2);
+            else if (p.gn_ng == 4) chunk_group_stats<4>(a, valid, lane, &s1, &s2);
+            else if (p.gn_ng == 2) chunk_group_stats<2>(a, valid, lane, &s1, &s2);
+            else chunk_group_stats<1>(a, valid, lane, &s1, &s2);
+            const int k = (c - member * 32) >> 6;
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++)
+              if (kk == k) {
+                csum[kk] += s1;
+                csq[kk] += s2;
+              }
+          }
         }
       } else if (!pair) {
         // generic path (partial N tiles, transposed / unaligned stores): 16 columns at a time
@@ -581,6 +667,18 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+    if (p.gn_acc != nullptr && st_img >= 0) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int cl = member * 32 + k * 64;
+        if (cl < out_cols_tile && (lane & (32 / p.gn_ng - 1)) == 0) {
+          const int g = ((st_nt * out_cols_tile + cl) >> 5) * p.gn_ng + lane / (32 / p.gn_ng);
+          double* dst = p.gn_acc + ((size_t)st_img * p.gn_groups + g) * 2;
+          atomicAdd(dst, (double)csum[k]);
+          atomicAdd(dst + 1, (double)csq[k]);
+        }
+      }
     }
   }
   tc_fence_before();
@@ -739,7 +837,7 @@ static void pick_tile(int H, int W, int* th, int* tw) {
   }
 }
 
-static int igemm_launch(const onedc_igemm_desc* d, cudaStream_t stream) {
+static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
   ONEDC_CHECK(d->ksize == 1 || d->ksize == 3, "igemm: ksize must be 1 or 3");
   ONEDC_CHECK(d->stride == 1 || (d->stride == 2 && d->ksize == 3), "igemm: stride 2 needs ksize 3");
   ONEDC_CHECK(d->a_c[0] > 0 && d->a_c[0] % 8 == 0 && d->a_c[1] % 8 == 0, "igemm: channels must be multiples of 8");
@@ -881,6 +979,20 @@ static int igemm_launch(const onedc_igemm_desc* d, cudaStream_t stream) {
     }
   }
 
+  p.gn_acc = nullptr;
+  d->gn_fused_out = 0;
+  if (d->gn_acc != nullptr && d->impl == 0 && !pair && p.splits == 1) {
+    const bool fast_all = p.vec_ok && (d->cout % p.BN == 0) && (p.BN % 32 == 0) &&
+                          (d->store_mode == ST_NORMAL || d->store_mode == ST_QUAD) && p.BN <= 256;
+    const int cpg = d->gn_groups > 0 ? d->cout / d->gn_groups : 0;
+    if (fast_all && d->gn_groups > 0 && d->cout % d->gn_groups == 0 && (cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32)) {
+      p.gn_acc = reinterpret_cast<double*>(d->gn_acc);
+      p.gn_ng = 32 / cpg;
+      p.gn_groups = d->gn_groups;
+      d->gn_fused_out = 1;
+    }
+  }
+
   if (d->impl == 1) {
     long long total = (long long)p.n_img * p.H * p.W * ((p.ncols_out + 15) / 16);
     int blocks = (int)((total + 127) / 128);
@@ -960,6 +1072,6 @@ static int igemm_launch(const onedc_igemm_desc* d, cudaStream_t stream) {
 
 }  // namespace onedc
 
-extern "C" int onedc_igemm(const onedc_igemm_desc* d, void* stream) {
+extern "C" int onedc_igemm(onedc_igemm_desc* d, void* stream) {
   return onedc::igemm_launch(d, reinterpret_cast<cudaStream_t>(stream));
 }

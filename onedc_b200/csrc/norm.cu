@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(256, 4) gn_stats_kernel(GnSrc s, long long hw,
 
 template <int VX>
 __global__ void __launch_bounds__(256, 4) gn_apply_kernel(GnSrc s, long long hw, int groups, const float* stats,
+                                                       const double* acc0, const double* acc1, float eps,
                                                        const float* gamma, const float* beta, int silu, void* out,
                                                        long long out_ld, int px_per_block) {
   constexpr int PY = 256 / VX;
@@ -212,13 +213,30 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(GnSrc s, long long hw,
   const int C = s.c0 + s.c1;
   const int v = blockIdx.x * VX + tx;
   const int n = blockIdx.z;
-  if (v * 8 >= C) return;
   const int cpg = C / groups;
+  __shared__ float gstat[64][2];
+  if (acc0 != nullptr) {
+    // statistics were accumulated per group by the producing igemm epilogue(s) (single source only)
+    if ((int)threadIdx.x < groups) {
+      const int g = threadIdx.x;
+      const double* src = acc0 + ((size_t)n * groups + g) * 2;
+      const double a = __ldcg(src), b = __ldcg(src + 1);
+      const double cnt = (double)hw * cpg;
+      const double mean = a / cnt;
+      double var = b / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      gstat[g][0] = (float)mean;
+      gstat[g][1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+  }
+  if (v * 8 >= C) return;
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) {
     const int c = v * 8 + j, g = c / cpg;
-    const float mean = stats[((long long)n * groups + g) * 2], rstd = stats[((long long)n * groups + g) * 2 + 1];
+    const float mean = acc0 != nullptr ? gstat[g][0] : stats[((long long)n * groups + g) * 2];
+    const float rstd = acc0 != nullptr ? gstat[g][1] : stats[((long long)n * groups + g) * 2 + 1];
     const float ga = gamma[c];
     sc[j] = rstd * ga;
     sh[j] = beta[c] - mean * rstd * ga;
@@ -398,8 +416,9 @@ extern "C" int onedc_groupnorm_stats(const void* x0, int32_t c0, int64_t ld0, co
 
 extern "C" int onedc_groupnorm_apply(const void* x0, int32_t c0, int64_t ld0, const void* x1, int32_t c1, int64_t ld1,
                                      int32_t in_dtype, int32_t n_img, int64_t hw, int32_t groups, const float* stats,
-                                     const float* gamma, const float* beta, int32_t silu, void* out, int64_t out_ld,
-                                     void* stream) {
+                                     const double* acc0, const double* acc1, float eps, const float* gamma,
+                                     const float* beta, int32_t silu, void* out, int64_t out_ld, void* stream) {
+  ONEDC_CHECK(stats != nullptr || (acc0 != nullptr && c1 == 0), "groupnorm_apply: no statistics");
   const int C = c0 + c1;
   ONEDC_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && C % groups == 0 && out_ld % 8 == 0, "groupnorm: bad channels");
   GnSrc s{x0, x1, c0, c1, ld0, ld1, in_dtype};
@@ -409,10 +428,10 @@ extern "C" int onedc_groupnorm_apply(const void* x0, int32_t c0, int64_t ld0, co
   ONEDC_CHECK(chunks <= 65535 && n_img <= 65535, "groupnorm: grid too large");
   if (nvec <= 16) {
     dim3 grid((nvec + 15) / 16, chunks, n_img);
-    gn_apply_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, groups, stats, gamma, beta, silu, out, out_ld, px);
+    gn_apply_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, groups, stats, acc0, acc1, eps, gamma, beta, silu, out, out_ld, px);
   } else {
     dim3 grid((nvec + 31) / 32, chunks, n_img);
-    gn_apply_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, groups, stats, gamma, beta, silu, out, out_ld, px);
+    gn_apply_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, groups, stats, acc0, acc1, eps, gamma, beta, silu, out, out_ld, px);
   }
   count_launch();
   ONEDC_CUDA(cudaGetLastError());

@@ -29,6 +29,7 @@ class IgemmDesc(C.Structure):
         ("splitk_ws", C.c_void_p), ("splitk_ws_floats", C.c_int64), ("splitk_counters", C.c_void_p),
         ("splitk_max_tiles", C.c_int32),
         ("ntaps", C.c_int32), ("tap_dy", C.c_int32 * 9), ("tap_dx", C.c_int32 * 9), ("quad", C.c_int32),
+        ("gn_acc", C.c_void_p), ("gn_groups", C.c_int32), ("gn_fused_out", C.c_int32),
     ]
 
 
@@ -43,8 +44,8 @@ PROTOTYPES = {
     "onedc_attention": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
     "onedc_groupnorm_ws_floats": (_i64, [_i32, _i64, _i32]),
     "onedc_groupnorm_stats": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
-    "onedc_groupnorm_apply": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _i32,
-                                        _vp, _i64, _vp]),
+    "onedc_groupnorm_apply": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _f32,
+                                        _vp, _vp, _i32, _vp, _i64, _vp]),
     "onedc_layernorm": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _i64, _vp]),
     "onedc_softmax_rows": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _f32, _vp, _i64, _vp]),
     "onedc_softmax_rows_batched": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _i32, _f32, _vp, _i64, _vp]),

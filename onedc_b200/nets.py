@@ -33,8 +33,9 @@ class DCB4:
     """DepthConvBlock4 = DepthConv (1x1+LReLU, dw3x3, 1x1 [+1x1 adaptor]) + ConvFFN3.
     5 launches: igemm, dwconv, igemm (adaptor folded in as a second K source), igemm (pair epilogue), igemm."""
 
-    def __init__(self, sd, p, cin, cout, dev):
+    def __init__(self, sd, p, cin, cout, dev, out_stats=False):
         self.cin, self.cout = cin, cout
+        self.out_stats = out_stats            # output feeds a GroupNorm: fuse its statistics into the last epilogue
         w, b = _wb(sd, p + ".block.0.conv1.0")
         self.conv1 = ConvW(w, b, dev)
         self.dw = DepthwiseW(sd[p + ".block.0.depth_conv.weight"].float(), sd[p + ".block.0.depth_conv.bias"].float(), dev)
@@ -55,7 +56,7 @@ class DCB4:
         else:
             h = igemm(t, self.conv2, res=x)
         f = igemm(h, self.ffn_in)
-        return igemm(f, self.ffn_out, res=h, out=out)
+        return igemm(f, self.ffn_out, res=h, out=out, stats=self.out_stats)
 
 
 class RBU:
@@ -82,8 +83,8 @@ class VQRes:
         self.c2 = ConvW(sd[p + ".conv2.weight"].float(), None, dev)
 
     def __call__(self, x, out=None):
-        h = igemm(self.n1(x), self.c1)
-        return igemm(self.n2(h), self.c2, res=x, out=out)
+        h = igemm(self.n1(x), self.c1, stats=True)
+        return igemm(self.n2(h), self.c2, res=x, out=out, stats=True)
 
 
 def _pad8(n):
@@ -111,7 +112,7 @@ class VQAttn:
         igemm(hn, self.v, store=ST_TRANSPOSED, out=vT)
         o = torch.empty((n, s, c), device=x.device, dtype=torch.bfloat16)
         ops.attention_unfused(qk[:, :, :c], qk[:, :, c:], vT, o, heads=1, head_dim=c, scale=float(c) ** -0.5)
-        return igemm(o.view(n, h, w, c), self.proj, res=x)
+        return igemm(o.view(n, h, w, c), self.proj, res=x, stats=True)
 
 
 class HyperSynthesis:
@@ -159,11 +160,12 @@ class SpatialPrior:
 class SemanticAdaptorNet:
     def __init__(self, sd, dev):
         p = "semantic_adaptor.to_semantic."
-        self.seq = [DCB4(sd, p + "0", 128, 768, dev), VQRes(sd, p + "1", 768, dev), VQAttn(sd, p + "2", 768, dev),
+        self.seq = [DCB4(sd, p + "0", 128, 768, dev, out_stats=True), VQRes(sd, p + "1", 768, dev), VQAttn(sd, p + "2", 768, dev),
                     VQAttn(sd, p + "3", 768, dev), VQRes(sd, p + "4", 768, dev), VQAttn(sd, p + "5", 768, dev),
                     VQAttn(sd, p + "6", 768, dev), DCB4(sd, p + "7", 768, 768, dev)]
 
     def __call__(self, z_sem):
+        ops.gn_arena_reset(z_sem.device)      # one zeroing of the fused-GroupNorm accumulators per pass
         t = z_sem
         for m in self.seq:
             t = m(t)
@@ -174,7 +176,7 @@ class LatentSynthesisNet:
     """Decoder g_s (codec_module.py:88-116): y_hat, y_semantic -> x_hat [N,h8,w8,320]."""
 
     def __init__(self, sd, dev):
-        self.tc = [DCB4(sd, "dec.trans_coding.0", 128, 512, dev), DCB4(sd, "dec.trans_coding.1", 512, 512, dev)]
+        self.tc = [DCB4(sd, "dec.trans_coding.0", 128, 512, dev), DCB4(sd, "dec.trans_coding.1", 512, 512, dev, out_stats=True)]
         self.res16 = [VQRes(sd, f"dec.blocks.{i}", 512, dev) for i in range(3)]
         self.up = ConvW(*pixshuf_permute(*_wb(sd, "dec.blocks.3")), dev)
         self.up_conv = ConvW(*_wb(sd, "dec.blocks.5"), dev)
@@ -182,7 +184,7 @@ class LatentSynthesisNet:
         self.sem = [RBU(sd, "dec.sem_up.0", 768, 512, dev), DCB4(sd, "dec.sem_up.1", 512, 512, dev),
                     RBU(sd, "dec.sem_up.2", 512, 256, dev), DCB4(sd, "dec.sem_up.3", 256, 256, dev),
                     RBU(sd, "dec.sem_up.4", 256, 256, dev)]
-        self.conv_out = DCB4(sd, "dec.conv_out", 512, 320, dev)
+        self.conv_out = DCB4(sd, "dec.conv_out", 512, 320, dev, out_stats=True)
 
     def alloc_cat(self, n, h16, w16, device):
         return torch.empty((n, 2 * h16, 2 * w16, 512), device=device, dtype=torch.bfloat16)
@@ -195,11 +197,12 @@ class LatentSynthesisNet:
         self.sem[-1](s, out=cat[..., 256:])
 
     def main_path(self, y_hat, cat):
+        ops.gn_arena_reset(y_hat.device)      # covers g_s, the UNet and the VAE decoder of this pass
         t = y_hat
         for m in self.tc + self.res16:
             t = m(t)
         t = igemm(t, self.up, store=ST_PIXSHUF, ps_c=512)
-        t = igemm(t, self.up_conv)
+        t = igemm(t, self.up_conv, stats=True)
         t = self.res8[0](t)
         t = self.res8[1](t)
         self.res8[2](t, out=cat[..., :256])
@@ -233,9 +236,9 @@ class UNetRes:
         self.sc = ConvW(*_wb(sd, p + ".conv_shortcut"), dev) if cin != cout else None
 
     def __call__(self, x, skip=None):
-        h = igemm(self.n1(x, skip), self.c1)
+        h = igemm(self.n1(x, skip), self.c1, stats=True)
         res = x if self.sc is None else igemm(x, self.sc, x2=skip)
-        return igemm(self.n2(h), self.c2, res=res)
+        return igemm(self.n2(h), self.c2, res=res, stats=True)
 
 
 class UNetTransformer:
@@ -296,7 +299,7 @@ class UNetTransformer:
         n3 = self.ln3(t)
         g = igemm(n3.view(b, 1, s, c), self.geglu)
         t = igemm(g, self.ff_out, res=t.view(b, 1, s, c))
-        return igemm(t.view(b, h, w, c), self.proj_out, res=x)
+        return igemm(t.view(b, h, w, c), self.proj_out, res=x, stats=True)
 
 
 class UNet:
@@ -349,9 +352,9 @@ class UNet:
         f32 = torch.float32
         # vae_reduction (fp32 outputs: this feeds the x0 formula, amplified by 1/sqrt(alpha_bar) ~ 14.6)
         sc = igemm(x, self.vr_sc, out_dtype=f32)
-        r = igemm(self.vr_n1(x), self.vr_c1)
+        r = igemm(self.vr_n1(x), self.vr_c1, stats=True)
         reduced = igemm(self.vr_n2(r), self.vr_c2, res=sc, out_dtype=f32)
-        h = igemm(x, self.conv_in)
+        h = igemm(x, self.conv_in, stats=True)
         stack = [h]
         for blk in self.down:
             for j, r_ in enumerate(blk["res"]):
@@ -360,7 +363,7 @@ class UNet:
                     h = blk["attn"][j](h, ctx)
                 stack.append(h)
             if "down" in blk:
-                h = igemm(h, blk["down"], stride=2)
+                h = igemm(h, blk["down"], stride=2, stats=True)
                 stack.append(h)
         h = self.mid_res[0](h)
         h = self.mid_attn(h, ctx)
@@ -391,9 +394,9 @@ class VAERes:
         self.sc = ConvW(*_wb(sd, p + ".conv_shortcut"), dev) if cin != cout else None
 
     def __call__(self, x):
-        h = igemm(self.n1(x), self.c1)
+        h = igemm(self.n1(x), self.c1, stats=True)
         res = x if self.sc is None else igemm(x, self.sc)
-        return igemm(self.n2(h), self.c2, res=res)
+        return igemm(self.n2(h), self.c2, res=res, stats=True)
 
 
 class VAEWindowAttention:
@@ -464,7 +467,7 @@ class VAEDecoder:
 
     def __call__(self, z_hilo):
         n, h, w, _ = z_hilo.shape
-        t = igemm(z_hilo, self.conv_in)
+        t = igemm(z_hilo, self.conv_in, stats=True)
         t = self.mid0(t)
         t = self.attn(t)
         t = self.mid1(t)

@@ -115,8 +115,14 @@ class UpConv:
     def __call__(self, x):
         n, h, w, c = x.shape
         out = torch.empty((n, 2 * h, 2 * w, self.cout), device=x.device, dtype=torch.bfloat16)
+        st = True
         for q, cw in enumerate(self.quads):
-            igemm(x, cw, out=out, store=ST_QUAD, quad=q)
+            igemm(x, cw, out=out, store=ST_QUAD, quad=q, stats=st)
+            st = getattr(out, "_gn_acc", None)
+            if st is None:
+                st = False
+        if st is False and hasattr(out, "_gn_acc"):
+            del out._gn_acc
         return out
 
 
@@ -160,7 +166,7 @@ def _splitk_buffers(device):
 
 
 def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None, out_dtype=torch.bfloat16,
-          store=ST_NORMAL, ps_c=0, w_batched=False, impl=None, quad=0):
+          store=ST_NORMAL, ps_c=0, w_batched=False, impl=None, quad=0, stats=False):
     """out = epilogue(conv(x [cat x2], wt)).  `out` may be a channel-slice view of a wider buffer."""
     lib = L.load()
     d = L.IgemmDesc()
@@ -216,9 +222,19 @@ def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None
     if SPLITK:
         ws, cnt = _splitk_buffers(x.device)
         d.splitk_ws, d.splitk_ws_floats, d.splitk_counters, d.splitk_max_tiles = ws.data_ptr(), ws.numel(), cnt.data_ptr(), cnt.numel()
+    acc = None
+    if stats is not False and GN_FUSED and d.impl == 0:
+        # stats=True: new accumulator slice; stats=<tensor>: keep accumulating into it (the 4 phases of an UpConv)
+        acc = _gn_arena_alloc(x.device, n * 32 * 2) if stats is True else stats
+        if acc is not None:
+            d.gn_acc, d.gn_groups = acc.data_ptr(), 32
     e0 = _prof_begin()
     L.check(lib.onedc_igemm(C.byref(d), _stream()), "onedc_igemm")
     _prof_end("igemm", e0, 2.0 * n * ho * wo * d.cout * (c0 + c1) * (d.ntaps if d.ntaps > 0 else d.ksize * d.ksize))
+    if acc is not None and d.gn_fused_out:
+        out._gn_acc = acc
+    elif hasattr(out, "_gn_acc"):
+        del out._gn_acc
     return out
 
 
@@ -264,6 +280,35 @@ def attention_unfused(q, k, vT, out, heads, head_dim, scale=None, valid=None):
 
 
 _gn_scratch = {}
+# fused GroupNorm statistics: igemm epilogues accumulate per-channel fp64 sums into slices of a per-(device, lane)
+# arena that is zeroed once per forward pass (gn_arena_reset); the consuming GroupNorm reads them instead of
+# launching the statistics kernel.  GN_FUSED = False forces the two-kernel route everywhere.
+GN_FUSED = os.environ.get("ONEDC_GN_FUSED", "1") == "1"
+_gn_arena = {}
+
+
+def gn_arena_reset(device):
+    key = (str(device), SCRATCH_LANE)
+    ar = _gn_arena.get(key)
+    if ar is None:
+        ar = _gn_arena[key] = {"buf": torch.zeros(1 << 22, device=device, dtype=torch.float64), "off": 0, "peak": 0}
+    if ar["off"] > 0:
+        ar["buf"][: ar["off"]].zero_()
+    ar["off"] = 0
+
+
+def _gn_arena_alloc(device, count):
+    key = (str(device), SCRATCH_LANE)
+    ar = _gn_arena.get(key)
+    if ar is None:
+        gn_arena_reset(device)
+        ar = _gn_arena[key]
+    count = (count + 15) // 16 * 16
+    if ar["off"] + count > ar["buf"].numel():
+        return None                                  # arena exhausted: caller falls back to the statistics kernel
+    v = ar["buf"][ar["off"]: ar["off"] + count]
+    ar["off"] += count
+    return v
 
 
 def _gn_buffers(device):
@@ -290,17 +335,24 @@ class GroupNorm:
             p1, _, _, _, c1, s1 = _nhwc(x2)
         hw, ct = h * w, c0 + c1
         assert n <= 256
-        acc, counters = _gn_buffers(x.device)
-        assert lib.onedc_groupnorm_ws_floats(n, hw, ct) <= acc.numel()
-        stats = torch.empty((n, self.groups, 2), device=x.device, dtype=torch.float32)
-        L.check(lib.onedc_groupnorm_stats(p0, c0, s0, p1, c1, s1, _dt(x), n, hw, self.groups, self.eps,
-                                          acc.data_ptr(), stats.data_ptr(), counters.data_ptr(),
-                                          0 if valid is None else valid.data_ptr(), _stream()), "groupnorm_stats")
+        a0 = getattr(x, "_gn_acc", None) if (GN_FUSED and valid is None and x2 is None and self.groups == 32) else None
+        a1 = None
+        fused = a0 is not None
+        stats_ptr = 0
+        if not fused:
+            acc, counters = _gn_buffers(x.device)
+            assert lib.onedc_groupnorm_ws_floats(n, hw, ct) <= acc.numel()
+            stats = torch.empty((n, self.groups, 2), device=x.device, dtype=torch.float32)
+            L.check(lib.onedc_groupnorm_stats(p0, c0, s0, p1, c1, s1, _dt(x), n, hw, self.groups, self.eps,
+                                              acc.data_ptr(), stats.data_ptr(), counters.data_ptr(),
+                                              0 if valid is None else valid.data_ptr(), _stream()), "groupnorm_stats")
+            stats_ptr = stats.data_ptr()
         if out is None:
             out = torch.empty((n, h, w, ct) if x.dim() == 4 else (n, hw, ct), device=x.device, dtype=torch.bfloat16)
         po, _, _, _, _, so = _nhwc(out)
-        L.check(lib.onedc_groupnorm_apply(p0, c0, s0, p1, c1, s1, _dt(x), n, hw, self.groups, stats.data_ptr(),
-                                          self.gamma.data_ptr(), self.beta.data_ptr(), 1 if silu else 0, po, so,
+        L.check(lib.onedc_groupnorm_apply(p0, c0, s0, p1, c1, s1, _dt(x), n, hw, self.groups, stats_ptr,
+                                          a0.data_ptr() if fused else 0, a1.data_ptr() if (fused and a1 is not None) else 0,
+                                          self.eps, self.gamma.data_ptr(), self.beta.data_ptr(), 1 if silu else 0, po, so,
                                           _stream()), "groupnorm_apply")
         return out
 

@@ -1,0 +1,75 @@
+"""BASELINE.json configs at full size on the GPU, checked through size-independent properties (the CPU oracle
+needs minutes at these sizes): lossless encode -> bytes -> decode round trip of the y symbols, bit-identical
+repeat decodes (graph replay vs eager), batch decode == single decode up to bf16 noise, finite output."""
+import time
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def model(cuda):
+    from onedc_b200 import weights as Wt
+    from onedc_b200.model import SD15_1step_codec_stage1
+    sds = (Wt.random_state_dict(Wt.unet_spec(), 0), Wt.random_state_dict(Wt.codec_spec(), 0),
+           Wt.random_state_dict(Wt.vae_spec(), 0))
+    m = SD15_1step_codec_stage1(state_dicts=sds, device=cuda)
+    m.codec_model.update(force=True)
+    return m
+
+
+def _roundtrip(model, h, w, seed):
+    from onedc_b200 import bitstream
+    enc, dec = [], []
+    stream, _ = model.codec_model.compress_synthetic(h, w, seed=seed, trace=enc)
+    d = bitstream.decode_i(stream)
+    model.codec_model._decompress_batch([d["bit_stream_y"]], [d["bit_stream_z"]], d["pad_height"], d["pad_width"], dec)
+    for k in range(4):
+        assert torch.equal(dec[k]["sym"].view(-1), enc[k]["sym"].view(-1)), f"step {k}: symbols not recovered"
+        assert torch.equal(dec[k]["y_hat"], enc[k]["y_hat"])
+    return stream
+
+
+def test_config2_single_768(model):
+    stream = _roundtrip(model, 768, 768, 11)
+    a = model.decode(stream=stream)
+    b = model.decode(stream=stream)
+    e = model.decode(stream=stream, stages={})
+    assert a.shape == (1, 3, 768, 768) and bool(torch.isfinite(a).all())
+    assert torch.equal(a, b)
+    mse = float(((a.clamp(-1, 1) - e.clamp(-1, 1)).double() ** 2).mean()) / 4
+    assert mse < 10 ** (-5.5), "graph replay and eager launches must agree up to bf16 rounding noise"
+    assert float(a.std()) > 1e-3
+
+
+def test_config3_batch_768x512(model):
+    streams = [_roundtrip(model, 512, 768, 100 + i) for i in range(4)]
+    singles = [model.decode(stream=s).clone() for s in streams]
+    batch = model.decode_batch(streams)
+    for s, b in zip(singles, batch):
+        assert b.shape == (1, 3, 512, 768)
+        mse = float(((s.clamp(-1, 1) - b.clamp(-1, 1)).double() ** 2).mean()) / 4
+        assert mse < 10 ** (-4.8), "batch decode deviates from single decode by more than bf16 noise"
+
+
+def test_config4_z_only_768(model, cuda):
+    z = torch.randint(0, 16384, (1, 12, 12), generator=torch.Generator().manual_seed(5), dtype=torch.int32)
+    a = model.decode_z_only(z)
+    b = model.decode_z_only(z)
+    assert a.shape == (1, 3, 768, 768) and bool(torch.isfinite(a).all()) and torch.equal(a, b)
+
+
+def test_config5_2048(model):
+    stream = _roundtrip(model, 2048, 2048, 21)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    a = model.decode(stream=stream, stages=None)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    b = model.decode(stream=stream)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"2048x2048: first decode (graph capture) {t1 - t0:.2f} s, replay {1e3 * (t2 - t1):.1f} ms, stream {len(stream)} B")
+    assert a.shape == (1, 3, 2048, 2048) and bool(torch.isfinite(a).all()) and torch.equal(a, b)

@@ -176,3 +176,26 @@ def test_quantize_residual_roundtrip(cuda):
         ops.dequant_accum(sym, means, dec, k)
     assert torch.equal(enc, dec)
     assert (enc.float() - y.float()).abs().max().item() <= 0.5 + 0.07     # half a quantisation step + bf16 rounding
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,two", [(1, 32, 32, 128, 128, False), (2, 64, 48, 128, 256, False), (1, 96, 96, 64, 512, False),
+                                                (1, 24, 24, 256, 320, True)])
+def test_groupnorm_statistics_fused_into_igemm(cuda, n, h, w, cin, cout, two):
+    """conv -> GroupNorm with the statistics accumulated by the conv's epilogue == the two-kernel GroupNorm."""
+    from onedc_b200 import ops
+    ops.gn_arena_reset(cuda)
+    x = _mk((n, h, w, cin), cuda, 1)
+    wt = torch.randn((cout, cin, 3, 3), generator=torch.Generator().manual_seed(2)) * (cin * 9) ** -0.5
+    cw = ops.ConvW(wt, torch.randn(cout, generator=torch.Generator().manual_seed(3)) * 0.3, cuda)
+    y = ops.igemm(x, cw, stats=True)
+    assert hasattr(y, "_gn_acc") == (not two), "fusion applies to 4/8/16/32 channels per group, single source"
+    y2 = ops.igemm(x, cw, stats=True) if two else None
+    c = cout * (2 if two else 1)
+    g = torch.Generator().manual_seed(4)
+    gn = ops.GroupNorm(1 + 0.1 * torch.randn(c, generator=g), 0.1 * torch.randn(c, generator=g), 1e-5, device=cuda)
+    fused = gn(y, y2)
+    plain = gn(y.clone(), None if y2 is None else y2.clone())          # clones carry no accumulators
+    ys = y.float() if y2 is None else torch.cat([y.float(), y2.float()], -1)
+    ref = F.silu(F.group_norm(ys.permute(0, 3, 1, 2), 32, gn.gamma, gn.beta, 1e-5)).permute(0, 2, 3, 1)
+    assert (fused.float() - ref).abs().max().item() < 3e-2
+    assert (fused.float() - plain.float()).abs().max().item() < 2e-2

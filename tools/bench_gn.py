@@ -21,7 +21,7 @@ for (h, w, c) in shapes:
                                           cnt.data_ptr(), 0, st))
 
     def f_apply():
-        L.check(lib.onedc_groupnorm_apply(x.data_ptr(), c, c, 0, 0, 0, 0, 1, h * w, 32, stats.data_ptr(), g.gamma.data_ptr(),
+        L.check(lib.onedc_groupnorm_apply(x.data_ptr(), c, c, 0, 0, 0, 0, 1, h * w, 32, stats.data_ptr(), 0, 0, 1e-6, g.gamma.data_ptr(),
                                           g.beta.data_ptr(), 1, out.data_ptr(), c, st))
 
     for name, fn in (("stats", f_stats), ("apply", f_apply)):
