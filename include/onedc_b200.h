@@ -97,7 +97,8 @@ typedef struct {
   int32_t store_mode;
   int32_t ps_c;
   int32_t bn;           /* N tile, multiple of 16 (32 for pair modes), <= 256; 0 = auto */
-  int32_t impl;         /* 0 = tcgen05 kernel, 1 = SIMT checking kernel (debug only) */
+  int32_t impl;         /* 0 = tcgen05 kernel, 1 = SIMT checking kernel (debug only), 2 = dry run: validate and
+                           decide (tiling, split-K, fused statistics) without launching (bench bookkeeping) */
   /* optional split-K scratch (layers with too few tiles to fill the GPU): fp32 workspace and per-tile int32
    * arrival counters that are zero on entry and zero again on exit; NULL disables split-K */
   void* splitk_ws;

@@ -866,7 +866,7 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
   p.BN = d->bn > 0 ? d->bn : pick_bn(d->cout, pair);
   ONEDC_CHECK(p.BN >= 16 && p.BN <= 256 && p.BN % (pair ? 32 : 16) == 0, "igemm: bad BN %d", p.BN);
   p.n_tiles = (d->cout + p.BN - 1) / p.BN;
-  if (d->bn <= 0 && !pair && d->impl == 0) {
+  if (d->bn <= 0 && !pair && d->impl != 1) {
     // few tiles and a short K loop (split-K will not apply): halve the N tile while that still fits one wave,
     // so twice as many SMs share the MMA work (A tiles are re-read from L2, which is cheap at these sizes)
     int th0, tw0;
@@ -969,7 +969,7 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
     const int octile = pair ? p.BN / 2 : p.BN;
     const bool fast_all = p.vec_ok && (d->cout % p.BN == 0) && (octile % 32 == 0) &&
                           (d->store_mode == ST_NORMAL || d->store_mode == ST_QUAD || (d->store_mode == ST_PIXSHUF && d->ps_c % 32 == 0));
-    if (d->impl == 0 && p.ws != nullptr && p.counters != nullptr && fast_all && tiles * 2 <= sm_count() &&
+    if (d->impl != 1 && p.ws != nullptr && p.counters != nullptr && fast_all && tiles * 2 <= sm_count() &&
         kiters >= 16 && tiles <= d->splitk_max_tiles / 2) {
       int s = sm_count() / tiles;
       if (s > kiters / 8) s = kiters / 8;
@@ -981,7 +981,7 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
 
   p.gn_acc = nullptr;
   d->gn_fused_out = 0;
-  if (d->gn_acc != nullptr && d->impl == 0 && !pair && p.splits == 1) {
+  if (d->gn_acc != nullptr && d->impl != 1 && !pair && p.splits == 1) {
     const bool fast_all = p.vec_ok && (d->cout % p.BN == 0) && (p.BN % 32 == 0) &&
                           (d->store_mode == ST_NORMAL || d->store_mode == ST_QUAD) && p.BN <= 256;
     const int cpg = d->gn_groups > 0 ? d->cout / d->gn_groups : 0;
@@ -1003,6 +1003,8 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
     ONEDC_CUDA(cudaGetLastError());
     return 0;
   }
+
+  if (d->impl == 2) return 0;          // dry run (bench): decisions only
 
   // ---- tensor maps
   CUtensorMap ma[2], mb;

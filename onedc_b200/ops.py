@@ -17,6 +17,9 @@ IMPL = int(os.environ.get("ONEDC_IMPL", "0"))
 ATTN = os.environ.get("ONEDC_ATTN", "flash")
 # when set to a list, igemm/attention append (name, start_event, end_event, algorithmic_flops) per launch
 PROFILE = None
+# bench-only: names of ops whose launches are skipped (outputs left uninitialised) so that the time of one kernel
+# family inside the graph-replayed step can be measured as a difference of two replays
+SKIP = set()
 
 
 def _prof_begin():
@@ -228,6 +231,13 @@ def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None
         acc = _gn_arena_alloc(x.device, n * 32 * 2) if stats is True else stats
         if acc is not None:
             d.gn_acc, d.gn_groups = acc.data_ptr(), 32
+    if PROFILE is not None:
+        taps_ = d.ntaps if d.ntaps > 0 else d.ksize * d.ksize
+        abytes = 2.0 * n * h * w * (c0 + c1) + 2.0 * d.cout * d.ktot * taps_ + out.element_size() * float(n * ho * wo * ncols) \
+            + (res.element_size() * float(res.numel()) if res is not None else 0.0)
+        PROFILE.append(("igemm_bytes", None, None, abytes))
+    if "igemm" in SKIP:
+        d.impl = 2                                   # dry run: same decisions (tiling, split-K, fused statistics), no launch
     e0 = _prof_begin()
     L.check(lib.onedc_igemm(C.byref(d), _stream()), "onedc_igemm")
     _prof_end("igemm", e0, 2.0 * n * ho * wo * d.cout * (c0 + c1) * (d.ntaps if d.ntaps > 0 else d.ksize * d.ksize))
@@ -248,6 +258,8 @@ def attention(q, k, v, out, heads, head_dim, scale=None, impl=None):
     assert b == 1 or (q.stride(0) == sq * q.stride(1) and k.stride(0) == skv * k.stride(1)
                       and v.stride(0) == skv * v.stride(1) and out.stride(0) == sq * out.stride(1))
     scale = head_dim ** -0.5 if scale is None else scale
+    if "attention" in SKIP:
+        return out
     e0 = _prof_begin()
     L.check(lib.onedc_attention(q.data_ptr(), q.stride(1), k.data_ptr(), v.data_ptr(), k.stride(1), out.data_ptr(),
                                 out.stride(1), b, heads, head_dim, sq, skv, scale, IMPL if impl is None else impl,
