@@ -71,6 +71,10 @@ const char* onedc_last_error(void);
 int onedc_version(void);
 /* number of kernels launched by this library in this process since the last reset */
 int64_t onedc_launch_count(int reset);
+/* programmatic dependent launch of every kernel of this library (default off: measured 3 % slower
+   inside the graph-replayed step on B200; env ONEDC_PDL=1 turns it on).
+   Returns the previous setting.  Takes effect for launches (and graph captures) made after the call. */
+int onedc_set_pdl(int on);
 
 /* ---- implicit-GEMM convolution / GEMM on tcgen05 ------------------------------------------ */
 typedef struct {
@@ -119,6 +123,11 @@ typedef struct {
   int32_t gn_fused_out;
 } onedc_igemm_desc;
 
+/* diagnostics: when set (device pointer to 148 x 16 int64, zeroed by the caller) every igemm CTA records clock
+   counters per warp role: [0] producer total, [1] producer waiting for a free A slot, [2] ... for a free B slot,
+   [4] MMA issuer total, [5] waiting for A data, [6] waiting for B data, [7] waiting for a free accumulator,
+   [9] epilogue waiting for a finished accumulator.  NULL turns it off. */
+void onedc_igemm_set_debug(void* dev_counters);
 int onedc_igemm(onedc_igemm_desc* d, void* stream);
 
 /* ---- flash attention on tcgen05 (multi-head, head_dim 40/80/160) -------------------------- */

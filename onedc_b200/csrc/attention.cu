@@ -71,6 +71,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();
   const uint32_t tmem_o = tmem_base + 2 * BKV;     // S buffers at columns [0, 2*BKV), O after them
 
   if (warp == 0) {
@@ -238,6 +239,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 __global__ void attention_simt_kernel(const __nv_bfloat16* q, long long q_ld, const __nv_bfloat16* k, const __nv_bfloat16* v,
                                       long long kv_ld, __nv_bfloat16* out, long long o_ld, int batch, int heads, int d,
                                       int sq, int skv, float scale) {
+  pdl_wait();
   const long long total = (long long)batch * heads * sq;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int s = (int)(i % sq);
@@ -283,10 +285,9 @@ extern "C" int onedc_attention(const void* q, int64_t q_ld, const void* k, const
     const long long total = (long long)batch * heads * sq;
     int blocks = (int)((total + 63) / 64);
     if (blocks > 148 * 32) blocks = 148 * 32;
-    attention_simt_kernel<<<blocks, 64, 0, st>>>((const __nv_bfloat16*)q, q_ld, (const __nv_bfloat16*)k,
+    ONEDC_CUDA(launch_k(attention_simt_kernel, blocks, 64, 0, st, (const __nv_bfloat16*)q, q_ld, (const __nv_bfloat16*)k,
                                                  (const __nv_bfloat16*)v, kv_ld, (__nv_bfloat16*)out, o_ld, batch, heads,
-                                                 head_dim, sq, skv, scale);
-    count_launch();
+                                                 head_dim, sq, skv, scale));
     ONEDC_CUDA(cudaGetLastError());
     return 0;
   }
@@ -326,8 +327,7 @@ extern "C" int onedc_attention(const void* q, int64_t q_ld, const void* k, const
     attr = smem;
   }
   dim3 grid((sq + 127) / 128, heads, batch);
-  attention_tc_kernel<<<grid, kAttnThreads, smem, st>>>(mq, mk, mv, p);
-  count_launch();
+  ONEDC_CUDA(launch_k(attention_tc_kernel, grid, kAttnThreads, smem, st, mq, mk, mv, p));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }

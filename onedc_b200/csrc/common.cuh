@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 namespace onedc {
 
@@ -33,6 +34,39 @@ void set_error(const char* fmt, ...);
 
 int sm_count();
 void count_launch();          // bumps the launch counter read by onedc_launch_count()
+bool pdl_enabled();           // programmatic dependent launch (default off; ONEDC_PDL=1 / onedc_set_pdl enable)
+
+// Programmatic dependent launch (opt-in).  With it every kernel of this library is launched with the
+// programmatic-stream-serialization attribute, so in a stream (or a captured graph) kernel i+1 may become resident while kernel i is still running:
+// its prologue (barrier init, TMEM allocation, descriptor prefetch, parameter math) overlaps the tail of kernel i.
+// Contract kept by every kernel here: ALL threads execute pdl_wait() before the first global-memory access that can
+// alias anything an earlier kernel reads or writes (which also makes the chain transitive).  pdl_trigger() is only
+// used late (igemm: after the CTA's last MMA is issued), never before a TMEM allocation: a dependent CTA that grabbed
+// TMEM first and then blocked in pdl_wait() would starve a co-resident CTA of the still-running primary.  Measured
+// on B200 (tools/micro/pdl_chain.cu): inside a graph an early trigger is slower than none; wait-only / late trigger
+// saves ~0.3 us per kernel boundary.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  count_launch();
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 __device__ __forceinline__ float act_apply(float v, int act, float slope) {
   switch (act) {

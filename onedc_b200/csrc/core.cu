@@ -1,5 +1,6 @@
 // Library plumbing: error string, device info, launch counter.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -29,11 +30,27 @@ int sm_count() {
   return n;
 }
 
+static std::atomic<int> g_pdl{-1};
+bool pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("ONEDC_PDL");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;      // opt-in: measured slower inside graphs on B200
+    g_pdl.store(v);
+  }
+  return v != 0;
+}
+
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 }  // namespace onedc
 
 extern "C" const char* onedc_last_error(void) { return onedc::g_err; }
+extern "C" int onedc_set_pdl(int on) {
+  const int old = onedc::pdl_enabled() ? 1 : 0;
+  onedc::g_pdl.store(on ? 1 : 0);
+  return old;
+}
 extern "C" int onedc_version(void) { return 100; }
 extern "C" int64_t onedc_launch_count(int reset) {
   long long v = onedc::g_launches.load();

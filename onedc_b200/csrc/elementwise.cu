@@ -20,6 +20,7 @@ __device__ __constant__ int kXor[4] = {0, 3, 2, 1};
 template <int C4>
 __global__ void __launch_bounds__(128) scale_to_index_kernel(const __nv_bfloat16* scales, long long ld, const uint8_t* lut,
                                                              int lo, int hi, int16_t* idx_out, int step, int h, int w) {
+  pdl_wait();
   __shared__ __align__(16) int16_t tile[C4][128 + 8];
   __shared__ uint8_t tab[2048];
   const long long hw = (long long)h * w;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(128) scale_to_index_kernel(const __nv_bfloat16
 // generic elementwise build_indexes (int32 out)
 __global__ void build_indexes_kernel(const void* scales, int dtype, const uint8_t* lut, const float* thr, int32_t* out,
                                      long long n) {
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     if (dtype == DT_BF16) {
       out[i] = __ldg(lut + reinterpret_cast<const uint16_t*>(scales)[i]);
@@ -95,6 +97,7 @@ template <int C4, int MODE>
 __global__ void __launch_bounds__(128) dequant_kernel(int16_t* sym, const __nv_bfloat16* yin, long long yin_ld,
                                                       const __nv_bfloat16* means, long long means_ld, __nv_bfloat16* y_hat,
                                                       long long y_ld, int step, int h, int w) {
+  pdl_wait();
   __shared__ __align__(16) int16_t tile[C4][128 + 8];
   const long long hw = (long long)h * w;
   const int n = blockIdx.y;
@@ -187,6 +190,7 @@ __global__ void __launch_bounds__(128) dequant_kernel(int16_t* sym, const __nv_b
 
 // ------------------------------------------------------------------------------------------------
 __global__ void fsq_codes_kernel(const int32_t* idx, __nv_bfloat16* out, long long n) {
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int v = idx[i];
     float c[8];
@@ -204,6 +208,7 @@ __global__ void fsq_codes_kernel(const int32_t* idx, __nv_bfloat16* out, long lo
 // depthwise 3x3, pad 1, NHWC bf16; weights fp32 [9][C], bias fp32 [C]
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const __nv_bfloat16* x, const float* w9c, const float* bias,
                                                         __nv_bfloat16* out, int n_img, int h, int w, int c) {
+  pdl_wait();
   const int nvec = c >> 3;
   const long long total = (long long)n_img * h * w * nvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -242,6 +247,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const __nv_bfloat16* x, 
 }
 
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* x, uint4* out, int n_img, int h, int w, int nvec) {
+  pdl_wait();
   const long long total = (long long)n_img * (2 * h) * (2 * w) * nvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i % nvec);
@@ -258,6 +264,7 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* x, uint4* 
 // enumerated row-major over its valid vh x vw extent, the rest of the window's rows are zero.
 __global__ void __launch_bounds__(256) window_partition_kernel(const uint4* x, uint4* out, int n_img, int h, int w, int nvec,
                                                                int win) {
+  pdl_wait();
   const int nwy = (h + win - 1) / win, nwx = (w + win - 1) / win;
   const long long total = (long long)n_img * nwy * nwx * win * win * nvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -281,6 +288,7 @@ __global__ void __launch_bounds__(256) window_partition_kernel(const uint4* x, u
 
 __global__ void __launch_bounds__(256) window_merge_kernel(const uint4* a, const uint4* res, uint4* out, int n_img, int h, int w,
                                                            int nvec, int win) {
+  pdl_wait();
   const int nwy = (h + win - 1) / win, nwx = (w + win - 1) / win;
   const long long total = (long long)n_img * h * w * nvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -311,6 +319,7 @@ struct PqW {
 };
 __global__ void x0_prepare_kernel(const float4* reduced, const float4* eps, float sa, float s1m, float inv_scaling, PqW pq,
                                   uint4* out_hilo, float4* x0_out, long long pixels) {
+  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels; i += (long long)gridDim.x * blockDim.x) {
     const float4 r = reduced[i], e = eps[i];
     float x0[4] = {(r.x - s1m * e.x) / sa, (r.y - s1m * e.y) / sa, (r.z - s1m * e.z) / sa, (r.w - s1m * e.w) / sa};
@@ -353,9 +362,8 @@ extern "C" int onedc_scale_to_index(const void* scales, int64_t ld, const uint8_
   ONEDC_CHECK(n_img <= 65535, "scale_to_index: batch too large");
   const long long hw = (long long)h * w;
   dim3 grid((unsigned)((hw + 127) / 128), n_img);
-  scale_to_index_kernel<32><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)scales, ld, lut, lut_lo, lut_hi, idx_out,
-                                                                     step, h, w);
-  count_launch();
+  ONEDC_CUDA(launch_k(scale_to_index_kernel<32>, grid, 128, 0, (cudaStream_t)stream, (const __nv_bfloat16*)scales, ld, lut, lut_lo, lut_hi, idx_out,
+                                                                     step, h, w));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -363,8 +371,7 @@ extern "C" int onedc_scale_to_index(const void* scales, int64_t ld, const uint8_
 extern "C" int onedc_build_indexes(const void* scales, int32_t in_dtype, const uint8_t* lut, const float* thresholds,
                                    int32_t* idx_out, int64_t n, void* stream) {
   ONEDC_CHECK((in_dtype == DT_BF16 && lut) || (in_dtype == DT_F32 && thresholds), "build_indexes: missing table");
-  build_indexes_kernel<<<ew_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(scales, in_dtype, lut, thresholds, idx_out, n);
-  count_launch();
+  ONEDC_CUDA(launch_k(build_indexes_kernel, ew_blocks(n, 256), 256, 0, (cudaStream_t)stream, scales, in_dtype, lut, thresholds, idx_out, n));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -374,10 +381,9 @@ extern "C" int onedc_dequant_accum(const int16_t* sym, const void* means, int64_
   ONEDC_CHECK(c4 == 32 && step >= 0 && step < 4 && means_ld % 8 == 0 && y_ld % 8 == 0, "dequant_accum: bad arguments");
   const long long hw = (long long)h * w;
   dim3 grid((unsigned)((hw + 127) / 128), n_img);
-  dequant_kernel<32, 0><<<grid, 128, 0, (cudaStream_t)stream>>>(const_cast<int16_t*>(sym), nullptr, 0,
+  ONEDC_CUDA(launch_k(dequant_kernel<32, 0>, grid, 128, 0, (cudaStream_t)stream, const_cast<int16_t*>(sym), nullptr, 0,
                                                                (const __nv_bfloat16*)means, means_ld,
-                                                               (__nv_bfloat16*)y_hat, y_ld, step, h, w);
-  count_launch();
+                                                               (__nv_bfloat16*)y_hat, y_ld, step, h, w));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -389,17 +395,15 @@ extern "C" int onedc_quantize_residual(const void* y, int64_t y_in_ld, const voi
               "quantize_residual: bad arguments");
   const long long hw = (long long)h * w;
   dim3 grid((unsigned)((hw + 127) / 128), n_img);
-  dequant_kernel<32, 1><<<grid, 128, 0, (cudaStream_t)stream>>>(sym, (const __nv_bfloat16*)y, y_in_ld,
+  ONEDC_CUDA(launch_k(dequant_kernel<32, 1>, grid, 128, 0, (cudaStream_t)stream, sym, (const __nv_bfloat16*)y, y_in_ld,
                                                                (const __nv_bfloat16*)means, means_ld,
-                                                               (__nv_bfloat16*)y_hat, y_ld, step, h, w);
-  count_launch();
+                                                               (__nv_bfloat16*)y_hat, y_ld, step, h, w));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int onedc_fsq_codes(const int32_t* idx, void* out, int64_t n, void* stream) {
-  fsq_codes_kernel<<<ew_blocks(n, 128), 128, 0, (cudaStream_t)stream>>>(idx, (__nv_bfloat16*)out, n);
-  count_launch();
+  ONEDC_CUDA(launch_k(fsq_codes_kernel, ew_blocks(n, 128), 128, 0, (cudaStream_t)stream, idx, (__nv_bfloat16*)out, n));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -408,9 +412,8 @@ extern "C" int onedc_dwconv3x3(const void* x, const float* w9c, const float* bia
                                int32_t w, int32_t c, void* stream) {
   ONEDC_CHECK(c % 8 == 0, "dwconv3x3: C must be a multiple of 8");
   const long long total = (long long)n_img * h * w * (c / 8);
-  dwconv3x3_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, w9c, bias,
-                                                                           (__nv_bfloat16*)out, n_img, h, w, c);
-  count_launch();
+  ONEDC_CUDA(launch_k(dwconv3x3_kernel, ew_blocks(total, 256), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, w9c, bias,
+                                                                           (__nv_bfloat16*)out, n_img, h, w, c));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -418,8 +421,7 @@ extern "C" int onedc_dwconv3x3(const void* x, const float* w9c, const float* bia
 extern "C" int onedc_upsample2x(const void* x, void* out, int32_t n_img, int32_t h, int32_t w, int32_t c, void* stream) {
   ONEDC_CHECK(c % 8 == 0, "upsample2x: C must be a multiple of 8");
   const long long total = (long long)n_img * 4 * h * w * (c / 8);
-  upsample2x_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, n_img, h, w, c / 8);
-  count_launch();
+  ONEDC_CUDA(launch_k(upsample2x_kernel, ew_blocks(total, 256), 256, 0, (cudaStream_t)stream, (const uint4*)x, (uint4*)out, n_img, h, w, c / 8));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -429,9 +431,8 @@ extern "C" int onedc_window_partition(const void* x, void* out, int32_t n_img, i
   ONEDC_CHECK(c % 8 == 0, "window_partition: C must be a multiple of 8");
   const int nwy = (h + win - 1) / win, nwx = (w + win - 1) / win;
   const long long total = (long long)n_img * nwy * nwx * win * win * (c / 8);
-  window_partition_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)out, n_img, h, w,
-                                                                                  c / 8, win);
-  count_launch();
+  ONEDC_CUDA(launch_k(window_partition_kernel, ew_blocks(total, 256), 256, 0, (cudaStream_t)stream, (const uint4*)x, (uint4*)out, n_img, h, w,
+                                                                                  c / 8, win));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -440,9 +441,8 @@ extern "C" int onedc_window_merge(const void* attn_out, const void* residual, vo
                                   int32_t c, int32_t win, void* stream) {
   ONEDC_CHECK(c % 8 == 0, "window_merge: C must be a multiple of 8");
   const long long total = (long long)n_img * h * w * (c / 8);
-  window_merge_kernel<<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)attn_out, (const uint4*)residual,
-                                                                              (uint4*)out, n_img, h, w, c / 8, win);
-  count_launch();
+  ONEDC_CUDA(launch_k(window_merge_kernel, ew_blocks(total, 256), 256, 0, (cudaStream_t)stream, (const uint4*)attn_out, (const uint4*)residual,
+                                                                              (uint4*)out, n_img, h, w, c / 8, win));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -453,10 +453,9 @@ extern "C" int onedc_x0_prepare(const float* reduced, const float* eps, float sq
   PqW pq;
   for (int i = 0; i < 16; i++) pq.w[i] = pq_w[i];   // host pointers: 4x4 weight + bias of post_quant_conv
   for (int i = 0; i < 4; i++) pq.b[i] = pq_b[i];
-  x0_prepare_kernel<<<ew_blocks(pixels, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)reduced, (const float4*)eps,
+  ONEDC_CUDA(launch_k(x0_prepare_kernel, ew_blocks(pixels, 256), 256, 0, (cudaStream_t)stream, (const float4*)reduced, (const float4*)eps,
                                                                              sqrt_alpha, sqrt_one_minus_alpha, inv_scaling,
-                                                                             pq, (uint4*)out_hilo, (float4*)x0_out, pixels);
-  count_launch();
+                                                                             pq, (uint4*)out_hilo, (float4*)x0_out, pixels));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }

@@ -19,6 +19,7 @@
 // The SIMT kernel at the bottom evaluates the same descriptor with scalar loops; it exists to check the
 // tensor-core kernel on the GPU (tests, impl = 1) and is never used by the decode path.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -43,6 +44,15 @@ struct IgemmParams {
   int tap_dc[9], tap_dx[9], tap_dp[9], tap_dy[9];
   int w_batched;
   int stages, stage_bytes;
+  // column-copy mode (stride-1 multi-tap convs, no split-K): the tile is a 16 x 8 pixel box; per 64-channel chunk the
+  // A operand is loaded ONCE per distinct tap column offset dx as a (16 + dy span) x 8 box (cm_rows x 1024 bytes),
+  // and every tap of that column reads it through a descriptor that starts (dy - min dy) * 1024 bytes into the box.
+  // A 3x3 conv moves 3 x 18/16 = 3.4 A tiles per chunk instead of 9: the L2->SM ingest (~70 B/clk/SM) is what bounds
+  // this kernel, not the tensor pipe.  A and B (weights) travel through separate rings.
+  int colmode, cm_groups, cm_dx[3], cm_nt[3], cm_tap[3][3], cm_row[3][3], cm_miny, cm_rows;
+  int a_slots, a_slot_bytes, b_slots, b_slot_bytes;
+  // optional per-CTA role timing (onedc_igemm_set_debug): 16 clock counters per CTA, see tools/igemm_roles.py
+  long long* dbg;
   // epilogue
   const float* bias;
   int epi_mode, act;
@@ -331,6 +341,17 @@ __device__ __forceinline__ void epi_finish32(const IgemmParams& p, float* a, con
   }
 }
 
+// mbarrier wait that adds the cycles spent waiting to *acc when role timing is on
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool timed, long long* acc) {
+  if (!timed) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  *acc += clock64() - t0;
+}
+
 // k-iteration index -> (tap, source, 64-channel chunk)
 struct KIter {
   int tap, src, kc;
@@ -352,10 +373,11 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t a_full[4];       // column-copy mode: the A ring (full_bar / empty_bar = B ring)
+  __shared__ __align__(8) uint64_t a_empty[4];
   __shared__ __align__(8) uint64_t tmem_full[2];
   __shared__ __align__(8) uint64_t tmem_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ int last_flag;
   __shared__ __align__(16) float bias_s[2][256];
 
   const int warp = threadIdx.x >> 5;
@@ -363,9 +385,13 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; s++) {
+    for (int s = 0; s < kMaxStages; s++) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 4; s++) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(&tmem_full[a], 1);
@@ -383,6 +409,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  pdl_wait();           // everything above overlapped the previous kernel's tail
 
   // work item = (tile, k-split); splits of one tile are adjacent items, i.e. run on different CTAs
   const int nsplit = SPLITK ? p.splits : 1;
@@ -393,9 +420,55 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (lane == 0 && !SPLITK && p.colmode) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      const int nch = p.kchunks[0] + p.kchunks[1];
+      uint8_t* smem_b = smem + (size_t)p.a_slots * p.a_slot_bytes;
+      const bool timed = p.dbg != nullptr;
+      long long w_a = 0, w_b = 0;
+      const long long t_start = clock64();
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        TileCoord t = decode_tile(p, item);
+        const int n0 = t.n_tile * p.BN;
+        for (int c = 0; c < nch; c++) {
+          const int src = c >= p.kchunks[0] ? 1 : 0;
+          const int kc = src ? c - p.kchunks[0] : c;
+          const CUtensorMap* ma = src ? &map_a1 : &map_a0;
+          const int kb = (src ? p.c1_off : 0) + kc * 64;
+          for (int g = 0; g < p.cm_groups; g++) {
+            mbar_wait_t(&a_empty[sa], pa ^ 1, timed, &w_a);
+            mbar_expect_tx(&a_full[sa], (uint32_t)p.a_slot_bytes);
+            tma_load_5d(smem + (size_t)sa * p.a_slot_bytes, ma, &a_full[sa], kc * 64, t.x0 + p.cm_dx[g], 0,
+                        t.y0 + p.cm_miny, t.img);
+            if (++sa == p.a_slots) {
+              sa = 0;
+              pa ^= 1;
+            }
+            for (int j = 0; j < p.cm_nt[g]; j++) {
+              mbar_wait_t(&empty_bar[sb], pb ^ 1, timed, &w_b);
+              mbar_expect_tx(&full_bar[sb], b_bytes);
+              tma_load_3d(smem_b + (size_t)sb * p.b_slot_bytes, &map_b, &full_bar[sb], kb, n0, p.cm_tap[g][j]);
+              if (++sb == p.b_slots) {
+                sb = 0;
+                pb ^= 1;
+              }
+            }
+          }
+        }
+      }
+      if (timed) {
+        long long* o = p.dbg + (size_t)blockIdx.x * 16;
+        o[0] = clock64() - t_start;
+        o[1] = w_a;
+        o[2] = w_b;
+      }
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const bool timed = p.dbg != nullptr;
+      long long w_b = 0;
+      const long long t_start = clock64();
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int tile = item / nsplit, split = item - tile * nsplit;
         TileCoord t = decode_tile(p, tile);
@@ -404,7 +477,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         for (int ki = k0; ki < k1; ki++) {
           const KIter k = decode_kiter(p, ki);
           const CUtensorMap* ma = k.src ? &map_a1 : &map_a0;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_t(&empty_bar[stage], phase ^ 1, timed, &w_b);
           uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
           uint8_t* sb = sa + kABytes;
           mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
@@ -418,23 +491,86 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           }
         }
       }
+      if (timed) {
+        long long* o = p.dbg + (size_t)blockIdx.x * 16;
+        o[0] = clock64() - t_start;
+        o[1] = 0;
+        o[2] = w_b;
+      }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && !SPLITK && p.colmode) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      const int nch = p.kchunks[0] + p.kchunks[1];
+      const uint32_t smem_a = smem_u32(smem);
+      const uint32_t smem_b = smem_a + (uint32_t)(p.a_slots * p.a_slot_bytes);
+      const bool timed = p.dbg != nullptr;
+      long long w_a = 0, w_b = 0, w_t = 0;
+      const long long t_start = clock64();
+      int it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, it++) {
+        const int acc = it & 1;
+        mbar_wait_t(&tmem_empty[acc], ((it >> 1) & 1) ^ 1, timed, &w_t);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        uint32_t accumulate = 0;
+        for (int c = 0; c < nch; c++) {
+          for (int g = 0; g < p.cm_groups; g++) {
+            mbar_wait_t(&a_full[sa], pa, timed, &w_a);
+            const uint32_t abase = smem_a + (uint32_t)(sa * p.a_slot_bytes);
+            for (int j = 0; j < p.cm_nt[g]; j++) {
+              mbar_wait_t(&full_bar[sb], pb, timed, &w_b);
+              tc_fence_after();
+              const uint64_t da = umma_smem_desc(abase + (uint32_t)p.cm_row[g][j] * 1024u, 16, 1024);
+              const uint64_t db = umma_smem_desc(smem_b + (uint32_t)(sb * p.b_slot_bytes), 16, 1024);
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
+                accumulate = 1;
+              }
+              umma_commit(&empty_bar[sb]);
+              if (++sb == p.b_slots) {
+                sb = 0;
+                pb ^= 1;
+              }
+            }
+            umma_commit(&a_empty[sa]);             // all taps of this column have read the box
+            if (++sa == p.a_slots) {
+              sa = 0;
+              pa ^= 1;
+            }
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+      if (timed) {
+        long long* o = p.dbg + (size_t)blockIdx.x * 16;
+        o[4] = clock64() - t_start;
+        o[5] = w_a;
+        o[6] = w_b;
+        o[7] = w_t;
+      }
+      pdl_trigger();
+    } else if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
+      const bool timed = p.dbg != nullptr;
+      long long w_b = 0, w_t = 0;
+      const long long t_start = clock64();
       int it = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, it++) {
         const int split = item % nsplit;
         const int k0 = (int)((long long)kiters * split / nsplit), k1 = (int)((long long)kiters * (split + 1) / nsplit);
         const int acc = it & 1;
-        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        mbar_wait_t(&tmem_empty[acc], ((it >> 1) & 1) ^ 1, timed, &w_t);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int ki = k0; ki < k1; ki++) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_t(&full_bar[stage], phase, timed, &w_b);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
           const uint64_t da = umma_smem_desc(sa, 16, 1024);
@@ -452,6 +588,14 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         }
         umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
       }
+      if (timed) {
+        long long* o = p.dbg + (size_t)blockIdx.x * 16;
+        o[4] = clock64() - t_start;
+        o[5] = 0;
+        o[6] = w_b;
+        o[7] = w_t;
+      }
+      pdl_trigger();    // this CTA's MMAs are all issued: the next kernel may start its prologue under our epilogue
     }
   } else {
     // ===================== epilogue warps =====================
@@ -477,7 +621,13 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       // stage this tile's bias slice (GEMM column order) in shared memory
       if (etid < p.BN) bias_s[acc][etid] = (p.bias != nullptr && n0 + etid < p.cout) ? __ldg(p.bias + n0 + etid) : 0.f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      if (p.dbg != nullptr && threadIdx.x == 64) {
+        const long long t0 = clock64();
+        mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+        p.dbg[(size_t)blockIdx.x * 16 + 9] += clock64() - t0;
+      } else {
+        mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      }
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
       const int o0 = t.n_tile * out_cols_tile;         // first output column of this tile
@@ -726,6 +876,7 @@ __device__ __forceinline__ void simt_dot16(const IgemmParams& p, int img, int y,
 }
 
 __global__ void igemm_simt_kernel(const __grid_constant__ IgemmParams p) {
+  pdl_wait();
   const int groups = (p.ncols_out + 15) / 16;
   const long long total = (long long)p.n_img * p.H * p.W * groups;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -836,6 +987,8 @@ static void pick_tile(int H, int W, int* th, int* tw) {
     }
   }
 }
+
+static long long* g_igemm_dbg = nullptr;
 
 static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
   ONEDC_CHECK(d->ksize == 1 || d->ksize == 3, "igemm: ksize must be 1 or 3");
@@ -979,6 +1132,58 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
     }
   }
 
+  // ---- column-copy mode: stride-1 multi-tap convs that do not split K (see IgemmParams)
+  p.colmode = 0;
+  {
+    static const bool colmode_on = getenv("ONEDC_COLMODE") == nullptr || getenv("ONEDC_COLMODE")[0] != '0';
+    if (colmode_on && d->impl != 1 && p.splits == 1 && d->stride == 1 && p.taps > 1 && !d->w_batched) {
+      int miny = 99, maxy = -99, ng = 0;
+      bool ok = true;
+      memset(p.cm_nt, 0, sizeof(p.cm_nt));
+      for (int t = 0; t < p.taps; t++) {
+        miny = p.tap_dy[t] < miny ? p.tap_dy[t] : miny;
+        maxy = p.tap_dy[t] > maxy ? p.tap_dy[t] : maxy;
+      }
+      for (int t = 0; t < p.taps && ok; t++) {
+        int g = 0;
+        while (g < ng && p.cm_dx[g] != p.tap_dx[t]) g++;
+        if (g == ng) {
+          if (ng == 3) {
+            ok = false;
+            break;
+          }
+          p.cm_dx[ng++] = p.tap_dx[t];
+        }
+        if (p.cm_nt[g] == 3) {
+          ok = false;
+          break;
+        }
+        p.cm_tap[g][p.cm_nt[g]] = t;
+        p.cm_row[g][p.cm_nt[g]] = p.tap_dy[t] - miny;
+        p.cm_nt[g]++;
+      }
+      if (ok && maxy - miny <= 2) {
+        p.cm_groups = ng;
+        p.cm_miny = miny;
+        p.cm_rows = 16 + maxy - miny;
+        p.a_slot_bytes = p.cm_rows * 1024;
+        p.b_slot_bytes = ((p.BN * 128 + 1023) / 1024) * 1024;
+        p.a_slots = p.BN <= 128 ? 4 : 3;
+        p.b_slots = (kSmemBudget - p.a_slots * p.a_slot_bytes) / p.b_slot_bytes;
+        if (p.b_slots > kMaxStages) p.b_slots = kMaxStages;
+        if (p.b_slots >= 3) {
+          p.colmode = 1;
+          p.TH = 16;
+          p.TW = 8;
+          p.tiles_y = (p.H + p.TH - 1) / p.TH;
+          p.tiles_x = (p.W + p.TW - 1) / p.TW;
+          p.m_tiles = p.n_img * p.tiles_y * p.tiles_x;
+        }
+      }
+    }
+  }
+
+  p.dbg = g_igemm_dbg;
   p.gn_acc = nullptr;
   d->gn_fused_out = 0;
   if (d->gn_acc != nullptr && d->impl != 1 && !pair && p.splits == 1) {
@@ -998,8 +1203,7 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
     int blocks = (int)((total + 127) / 128);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    igemm_simt_kernel<<<blocks, 128, 0, stream>>>(p);
-    count_launch();
+    ONEDC_CUDA(launch_k(igemm_simt_kernel, blocks, 128, 0, stream, p));
     ONEDC_CUDA(cudaGetLastError());
     return 0;
   }
@@ -1017,7 +1221,7 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
     ONEDC_CHECK(reinterpret_cast<uintptr_t>(d->a_ptr[s]) % 16 == 0, "igemm: A pointer must be 16-byte aligned");
     const uint64_t S = (uint64_t)d->a_pix_stride[s];
     uint64_t dims[5], str[4];
-    uint32_t box[5] = {64, (uint32_t)p.TW, 1, (uint32_t)p.TH, 1};
+    uint32_t box[5] = {64, (uint32_t)p.TW, 1, (uint32_t)(p.colmode ? p.cm_rows : p.TH), 1};
     if (d->stride == 1) {
       dims[0] = (uint64_t)d->a_c[s];
       dims[1] = (uint64_t)d->w_in;
@@ -1054,7 +1258,8 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
   }
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
   int grid = total_tiles < sm_count() ? total_tiles : sm_count();
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  const size_t smem = (p.colmode ? (size_t)p.a_slots * p.a_slot_bytes + (size_t)p.b_slots * p.b_slot_bytes
+                                 : (size_t)p.stages * p.stage_bytes) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     ONEDC_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1064,15 +1269,16 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
     attr_set = true;
   }
   if (p.splits > 1)
-    igemm_tc_kernel<true><<<grid, kThreads, smem, stream>>>(ma[0], ma[1], mb, p);
+    ONEDC_CUDA(launch_k(igemm_tc_kernel<true>, grid, kThreads, smem, stream, ma[0], ma[1], mb, p));
   else
-    igemm_tc_kernel<false><<<grid, kThreads, smem, stream>>>(ma[0], ma[1], mb, p);
-  count_launch();
+    ONEDC_CUDA(launch_k(igemm_tc_kernel<false>, grid, kThreads, smem, stream, ma[0], ma[1], mb, p));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }
 
 }  // namespace onedc
+
+extern "C" void onedc_igemm_set_debug(void* dev_counters) { onedc::g_igemm_dbg = reinterpret_cast<long long*>(dev_counters); }
 
 extern "C" int onedc_igemm(onedc_igemm_desc* d, void* stream) {
   return onedc::igemm_launch(d, reinterpret_cast<cudaStream_t>(stream));

@@ -55,6 +55,7 @@ template <int VX>
 __global__ void __launch_bounds__(256, 4) gn_stats_kernel(GnSrc s, long long hw, int chunk_px, int groups, float eps,
                                                        float* part, float* stats, unsigned int* counters,
                                                        const int* valid_px) {
+  pdl_wait();
   constexpr int PY = 256 / VX;
   __shared__ float red[PY][VX][16];
   __shared__ float chan[VX * 8][2];
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(GnSrc s, long long hw,
                                                        const double* acc0, const double* acc1, float eps,
                                                        const float* gamma, const float* beta, int silu, void* out,
                                                        long long out_ld, int px_per_block) {
+  pdl_wait();
   constexpr int PY = 256 / VX;
   const int tx = threadIdx.x % VX, ty = threadIdx.x / VX;
   const int C = s.c0 + s.c1;
@@ -288,6 +290,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(GnSrc s, long long hw,
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* x, long long ld, long long rows, int c,
                                                         const float* gamma, const float* beta, float eps,
                                                         __nv_bfloat16* out, long long out_ld) {
+  pdl_wait();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31, nvec = c >> 3;
@@ -336,6 +339,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* x, 
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* s, long long ld, long long rows, int cols, int valid,
                                                            const int* valid_per_batch, int rows_per_batch, float scale,
                                                            __nv_bfloat16* out, long long out_ld) {
+  pdl_wait();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -406,10 +410,9 @@ extern "C" int onedc_groupnorm_stats(const void* x0, int32_t c0, int64_t ld0, co
   ONEDC_CHECK(chunks <= 65535 && n_img <= 65535, "groupnorm: grid too large");
   dim3 grid(slabs, chunks, n_img);
   if (vx == 16)
-    gn_stats_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, px, groups, eps, partial, stats, counters, valid_px);
+    ONEDC_CUDA(launch_k(gn_stats_kernel<16>, grid, 256, 0, (cudaStream_t)stream, s, hw, px, groups, eps, partial, stats, counters, valid_px));
   else
-    gn_stats_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, px, groups, eps, partial, stats, counters, valid_px);
-  count_launch();
+    ONEDC_CUDA(launch_k(gn_stats_kernel<32>, grid, 256, 0, (cudaStream_t)stream, s, hw, px, groups, eps, partial, stats, counters, valid_px));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -428,12 +431,11 @@ extern "C" int onedc_groupnorm_apply(const void* x0, int32_t c0, int64_t ld0, co
   ONEDC_CHECK(chunks <= 65535 && n_img <= 65535, "groupnorm: grid too large");
   if (nvec <= 16) {
     dim3 grid((nvec + 15) / 16, chunks, n_img);
-    gn_apply_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, groups, stats, acc0, acc1, eps, gamma, beta, silu, out, out_ld, px);
+    ONEDC_CUDA(launch_k(gn_apply_kernel<16>, grid, 256, 0, (cudaStream_t)stream, s, hw, groups, stats, acc0, acc1, eps, gamma, beta, silu, out, out_ld, px));
   } else {
     dim3 grid((nvec + 31) / 32, chunks, n_img);
-    gn_apply_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(s, hw, groups, stats, acc0, acc1, eps, gamma, beta, silu, out, out_ld, px);
+    ONEDC_CUDA(launch_k(gn_apply_kernel<32>, grid, 256, 0, (cudaStream_t)stream, s, hw, groups, stats, acc0, acc1, eps, gamma, beta, silu, out, out_ld, px));
   }
-  count_launch();
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -442,9 +444,8 @@ extern "C" int onedc_layernorm(const void* x, int64_t ld, int64_t rows, int32_t 
                                float eps, void* out, int64_t out_ld, void* stream) {
   ONEDC_CHECK(c % 8 == 0 && c <= 1280 && ld % 8 == 0 && out_ld % 8 == 0, "layernorm: C must be a multiple of 8, <= 1280");
   const int blocks = (int)((rows + 7) / 8);
-  layernorm_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ld, rows, c, gamma, beta, eps,
-                                                             (__nv_bfloat16*)out, out_ld);
-  count_launch();
+  ONEDC_CUDA(launch_k(layernorm_kernel, blocks, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, ld, rows, c, gamma, beta, eps,
+                                                             (__nv_bfloat16*)out, out_ld));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -452,9 +453,8 @@ extern "C" int onedc_layernorm(const void* x, int64_t ld, int64_t rows, int32_t 
 extern "C" int onedc_softmax_rows(const float* scores, int64_t ld, int64_t rows, int32_t cols, int32_t valid, float scale,
                                   void* out, int64_t out_ld, void* stream) {
   const int blocks = (int)((rows + 7) / 8);
-  softmax_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(scores, ld, rows, cols, valid, nullptr, 1, scale,
-                                                                (__nv_bfloat16*)out, out_ld);
-  count_launch();
+  ONEDC_CUDA(launch_k(softmax_rows_kernel, blocks, 256, 0, (cudaStream_t)stream, scores, ld, rows, cols, valid, nullptr, 1, scale,
+                                                                (__nv_bfloat16*)out, out_ld));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -463,9 +463,8 @@ extern "C" int onedc_softmax_rows_batched(const float* scores, int64_t ld, int64
                                           const int32_t* valid_per_batch, int32_t rows_per_batch, float scale, void* out,
                                           int64_t out_ld, void* stream) {
   const int blocks = (int)((rows + 7) / 8);
-  softmax_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(scores, ld, rows, cols, cols, valid_per_batch,
-                                                                rows_per_batch, scale, (__nv_bfloat16*)out, out_ld);
-  count_launch();
+  ONEDC_CUDA(launch_k(softmax_rows_kernel, blocks, 256, 0, (cudaStream_t)stream, scores, ld, rows, cols, cols, valid_per_batch,
+                                                                rows_per_batch, scale, (__nv_bfloat16*)out, out_ld));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }

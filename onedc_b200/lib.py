@@ -40,7 +40,9 @@ PROTOTYPES = {
     "onedc_last_error": (C.c_char_p, []),
     "onedc_version": (C.c_int, []),
     "onedc_launch_count": (_i64, [C.c_int]),
+    "onedc_set_pdl": (C.c_int, [C.c_int]),
     "onedc_igemm": (C.c_int, [C.POINTER(IgemmDesc), _vp]),
+    "onedc_igemm_set_debug": (None, [_vp]),
     "onedc_attention": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
     "onedc_groupnorm_ws_floats": (_i64, [_i32, _i64, _i32]),
     "onedc_groupnorm_stats": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
@@ -101,6 +103,11 @@ def check(rc, what=""):
     if rc != 0:
         msg = load().onedc_last_error()
         raise OnedcError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def set_pdl(on):
+    """Programmatic dependent launch on/off for subsequent launches and graph captures; returns the old setting."""
+    return bool(load().onedc_set_pdl(1 if on else 0))
 
 
 def launch_count(reset=False):

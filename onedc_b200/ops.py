@@ -17,6 +17,8 @@ IMPL = int(os.environ.get("ONEDC_IMPL", "0"))
 ATTN = os.environ.get("ONEDC_ATTN", "flash")
 # when set to a list, igemm/attention append (name, start_event, end_event, algorithmic_flops) per launch
 PROFILE = None
+# when PROFILE is on and this is a list, igemm appends one shape record per launch (tools/layer_table.py)
+PROFILE_INFO = None
 # bench-only: names of ops whose launches are skipped (outputs left uninitialised) so that the time of one kernel
 # family inside the graph-replayed step can be measured as a difference of two replays
 SKIP = set()
@@ -238,6 +240,9 @@ def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None
         PROFILE.append(("igemm_bytes", None, None, abytes))
     if "igemm" in SKIP:
         d.impl = 2                                   # dry run: same decisions (tiling, split-K, fused statistics), no launch
+    if PROFILE_INFO is not None:
+        PROFILE_INFO.append(dict(n=n, h=h, w=w, cin=c0 + c1, cout=d.cout, taps=d.ntaps if d.ntaps > 0 else d.ksize * d.ksize,
+                                 stride=stride, epi=d.epi_mode, store=store, res=res is not None, f32=out.dtype == torch.float32))
     e0 = _prof_begin()
     L.check(lib.onedc_igemm(C.byref(d), _stream()), "onedc_igemm")
     _prof_end("igemm", e0, 2.0 * n * ho * wo * d.cout * (c0 + c1) * (d.ntaps if d.ntaps > 0 else d.ksize * d.ksize))
@@ -328,7 +333,7 @@ def _gn_buffers(device):
     key = (str(device), SCRATCH_LANE)
     if key not in _gn_scratch:
         _gn_scratch[key] = (torch.empty(1 << 20, device=device, dtype=torch.float32),     # block partial sums
-                            torch.zeros(256, device=device, dtype=torch.int32))
+                            torch.zeros(8192, device=device, dtype=torch.int32))
     return _gn_scratch[key]
 
 
@@ -346,7 +351,7 @@ class GroupNorm:
         if x2 is not None:
             p1, _, _, _, c1, s1 = _nhwc(x2)
         hw, ct = h * w, c0 + c1
-        assert n <= 256
+        assert n <= 8192
         a0 = getattr(x, "_gn_acc", None) if (GN_FUSED and valid is None and x2 is None and self.groups == 32) else None
         a1 = None
         fused = a0 is not None

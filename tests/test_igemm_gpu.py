@@ -194,3 +194,33 @@ def test_folded_upsample_conv(cuda, n, h, w, c, co):
     o1 = torch.zeros_like(out)
     ops.igemm(x, cw, out=o1, store=ops.ST_QUAD, quad=3, impl=1)
     _close(o1[:, 1::2, 1::2], ref[:, 1::2, 1::2])
+
+
+@pytest.mark.parametrize("n,h,w,cin,cin2,cout", [
+    (1, 40, 36, 64, 0, 96), (1, 96, 96, 256, 0, 256), (2, 50, 30, 128, 0, 128), (1, 17, 9, 192, 0, 64),
+    (1, 192, 160, 128, 0, 128), (1, 96, 96, 320, 320, 320), (1, 64, 64, 72, 40, 48), (3, 33, 65, 64, 0, 512)])
+def test_column_copy_mode_3x3(cuda, n, h, w, cin, cin2, cout):
+    """Stride-1 3x3 convs without split-K run in column-copy mode (16x8 pixel tiles, one A box per tap column, separate
+    A / B rings): ragged edges, several tiles per CTA (ring phase wrap), two concatenated sources, bias, residual and
+    the fused GroupNorm statistics must all match torch and the SIMT checker."""
+    from onedc_b200 import ops
+    x = _mk((n, h, w, cin), cuda, 1)
+    x2 = _mk((n, h, w, cin2), cuda, 5) if cin2 else None
+    ct = cin + cin2
+    wt = _mk((cout, ct, 3, 3), "cpu", 2, scale=(ct * 9) ** -0.5).float()
+    b = _mk((cout,), "cpu", 3).float()
+    res = _mk((n, h, w, cout), cuda, 4)
+    cw = ops.ConvW(wt, b, cuda)
+    ops.gn_arena_reset(cuda)
+    out = ops.igemm(x, cw, x2=x2, res=res, stats=True)
+    ref = _ref_conv(x, cw.w.float().reshape(3, 3, cout, -1).permute(2, 3, 0, 1)[:, :ct].contiguous(), b.to(cuda), 3, 1, x2) + res.float()
+    _close(out, ref)
+    _close(ops.igemm(x, cw, x2=x2, res=res, impl=1), ref)
+    assert torch.equal(out, ops.igemm(x, cw, x2=x2, res=res)), "not deterministic"
+    acc = getattr(out, "_gn_acc", None)
+    if acc is not None:                          # fused statistics: per (image, group) sum and sum of squares
+        torch.cuda.synchronize()
+        got = acc[: n * 32 * 2].view(n, 32, 2)
+        o = out.float().view(n, h * w, 32, cout // 32)
+        want = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1).double()
+        assert torch.allclose(got, want, rtol=2e-3, atol=1e-2 * float(want.abs().max()) * 1e-2)

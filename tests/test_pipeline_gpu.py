@@ -179,3 +179,25 @@ def test_sizes_with_edge_windows_and_padding(bundle, hh, ww):
     assert p >= 45.0
     g = model.decode(stream=stream)                       # graph route
     assert _psnr01(g.cpu(), img.cpu()) > 55 and torch.equal(g, model.decode(stream=stream))
+
+
+def test_programmatic_dependent_launch_is_bit_identical(bundle):
+    """Every kernel is launched with the programmatic-stream-serialization attribute (kernel i+1's prologue overlaps
+    kernel i's tail).  Early starts must never change a result: graphs captured with PDL off and on give the same
+    bits, replay after replay."""
+    from onedc_b200 import lib
+    from onedc_b200.graphs import GraphedDecoder
+    model = bundle["model"]
+    outs = []
+    old = lib.set_pdl(False)
+    try:
+        for on in (False, True):
+            lib.set_pdl(on)
+            gd = GraphedDecoder(model, 1, H, W)
+            for _ in range(3):
+                host, _ = gd.decode([bundle["stream"]])
+                outs.append(host.clone())
+    finally:
+        lib.set_pdl(old)
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0]), "PDL changed the decoded image"

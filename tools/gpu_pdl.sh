@@ -1,0 +1,20 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out; OUT=gpurun_out
+for f in test_elementwise_gpu test_igemm_gpu test_attention_gpu test_pipeline_gpu test_configs_gpu; do
+  echo "== $f"
+  timeout 900 python -m pytest tests/$f.py -q -m gpu -x --tb=short > $OUT/$f.txt 2>&1
+  echo "rc=$?" >> $OUT/$f.txt
+  tail -3 $OUT/$f.txt
+done
+for pdl in 0 1; do
+  ONEDC_PDL=$pdl timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $OUT/bench_pdl$pdl.txt 2> $OUT/bench_pdl$pdl.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open("$OUT/bench_pdl$pdl.txt").read().strip().splitlines()[-1])
+    print("pdl=$pdl value", round(d["value"],2), "ms", round(d["ms_per_step"],3), "e2e ms", round(d["e2e"]["ms_per_step"],3), "igemm ms", round(d["roofline"]["kernel_ms_per_step"],3), "frac", round(d["roofline"]["frac"],3), "attn", round(d["roofline"]["attention"]["ms_per_step"],3))
+except Exception as e:
+    print("bench pdl=$pdl failed", e); print(open("$OUT/bench_pdl$pdl.err").read()[-1500:])
+PY
+done

@@ -1,0 +1,28 @@
+"""Where does an igemm CTA spend its time?  Per-role clock counters (onedc_igemm_set_debug) for one layer shape.
+    python tools/igemm_roles.py n h w cin cout k"""
+import ctypes as C
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from onedc_b200 import lib, ops
+
+n, h, w, cin, cout, k = [int(v) for v in sys.argv[1:7]]
+dev = torch.device("cuda:0")
+x = torch.randn((n, h, w, cin), device=dev).to(torch.bfloat16)
+wt = torch.randn((cout, cin, k, k)) * (cin * k * k) ** -0.5
+cw = ops.ConvW(wt, torch.zeros(cout), dev)
+out = torch.empty((n, h, w, cout), device=dev, dtype=torch.bfloat16)
+for _ in range(3):
+    ops.igemm(x, cw, out=out)
+torch.cuda.synchronize()
+dbg = torch.zeros((148, 16), device=dev, dtype=torch.int64)
+lib.load().onedc_igemm_set_debug(C.c_void_p(dbg.data_ptr()))
+ops.igemm(x, cw, out=out)
+torch.cuda.synchronize()
+lib.load().onedc_igemm_set_debug(C.c_void_p(0))
+d = dbg.double().mean(0).tolist()
+names = {0: "producer total", 1: "  waits free A slot", 2: "  waits free B slot", 4: "MMA issuer total", 5: "  waits A data",
+         6: "  waits B data", 7: "  waits free accumulator", 9: "epilogue waits accumulator"}
+print(f"{n}x{h}x{w} {cin}->{cout} k{k}  colmode={os.environ.get('ONEDC_COLMODE', '1')}  (mean clocks per CTA)")
+for i, nm in names.items():
+    print(f"  {nm:28s} {d[i]:10.0f}")
