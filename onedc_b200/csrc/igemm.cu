@@ -341,14 +341,15 @@ __device__ __forceinline__ void epi_finish32(const IgemmParams& p, float* a, con
   }
 }
 
-// mbarrier wait that adds the cycles spent waiting to *acc when role timing is on
-__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, bool timed, long long* acc) {
-  if (!timed) {
-    mbar_wait(bar, parity);
+// mbarrier wait on a shared-memory ADDRESS; adds the cycles spent waiting to *acc when role timing is compiled in
+template <bool TIMED>
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long* acc) {
+  if (!TIMED) {
+    mbar_wait_a(bar, parity);
     return;
   }
   const long long t0 = clock64();
-  mbar_wait(bar, parity);
+  mbar_wait_a(bar, parity);
   *acc += clock64() - t0;
 }
 
@@ -366,7 +367,7 @@ __device__ __forceinline__ KIter decode_kiter(const IgemmParams& p, int ki) {
   return k;
 }
 
-template <bool SPLITK>
+template <bool SPLITK, bool TIMED>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ IgemmParams p) {
@@ -380,7 +381,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float bias_s[2][256];
 
-  const int warp = threadIdx.x >> 5;
+  // broadcast from lane 0 so that the compiler KNOWS the warp index is warp-uniform (role branches stay uniform)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -418,185 +420,216 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   const uint32_t a_bytes = (uint32_t)(p.TH * p.TW) * 128u;
   const uint32_t b_bytes = (uint32_t)p.BN * 128u;
 
+  // The producer and the MMA issuer are single-lane jobs, but their loops are executed by the WHOLE warp with only
+  // the TMA / MMA / commit instructions under `if (leader)`, and every ring address (slot, barrier, descriptor) is a
+  // register that is bumped by a constant per step.  The loop state then lives in uniform registers and ptxas emits
+  // bare UTMALDG / UTCHMMA: ~35 scalar instructions per k-step.  (A loop entered under `if (lane == 0)` with
+  // barrier[stage] indexing cost ~100 clocks of scalar latency per MMA, which bounded every layer with N <= 128.)
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+  const uint32_t afull0 = smem_u32(&a_full[0]), aempty0 = smem_u32(&a_empty[0]);
+  const uint32_t tfull0 = smem_u32(&tmem_full[0]), tempty0 = smem_u32(&tmem_empty[0]);
+  const uint32_t smem0 = smem_u32(smem);
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0 && !SPLITK && p.colmode) {
+    const uint32_t leader = elect_one();
+    long long w_a = 0, w_b = 0;
+    const long long t_start = TIMED ? clock64() : 0;
+    const int nch = p.kchunks[0] + p.kchunks[1], kch0 = p.kchunks[0], c1_off = p.c1_off;
+    if (!SPLITK && p.colmode) {
+      const int a_slots = p.a_slots, b_slots = p.b_slots, groups = p.cm_groups;
+      const uint32_t a_sz = (uint32_t)p.a_slot_bytes, b_sz = (uint32_t)p.b_slot_bytes;
+      const uint32_t smem_b0 = smem0 + (uint32_t)a_slots * a_sz;
       int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      const int nch = p.kchunks[0] + p.kchunks[1];
-      uint8_t* smem_b = smem + (size_t)p.a_slots * p.a_slot_bytes;
-      const bool timed = p.dbg != nullptr;
-      long long w_a = 0, w_b = 0;
-      const long long t_start = clock64();
+      uint32_t pa = 1, pb = 1;                       // parity to wait for on the EMPTY barriers
+      uint32_t a_dst = smem0, b_dst = smem_b0, a_fb = afull0, a_eb = aempty0, b_fb = full0, b_eb = empty0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        TileCoord t = decode_tile(p, item);
+        const TileCoord t = decode_tile(p, item);
         const int n0 = t.n_tile * p.BN;
+        const int ay = t.y0 + p.cm_miny;
         for (int c = 0; c < nch; c++) {
-          const int src = c >= p.kchunks[0] ? 1 : 0;
-          const int kc = src ? c - p.kchunks[0] : c;
+          const int src = c >= kch0 ? 1 : 0;
+          const int kc = src ? c - kch0 : c;
           const CUtensorMap* ma = src ? &map_a1 : &map_a0;
-          const int kb = (src ? p.c1_off : 0) + kc * 64;
-          for (int g = 0; g < p.cm_groups; g++) {
-            mbar_wait_t(&a_empty[sa], pa ^ 1, timed, &w_a);
-            mbar_expect_tx(&a_full[sa], (uint32_t)p.a_slot_bytes);
-            tma_load_5d(smem + (size_t)sa * p.a_slot_bytes, ma, &a_full[sa], kc * 64, t.x0 + p.cm_dx[g], 0,
-                        t.y0 + p.cm_miny, t.img);
-            if (++sa == p.a_slots) {
-              sa = 0;
-              pa ^= 1;
+          const int kb = (src ? c1_off : 0) + kc * 64;
+          for (int g = 0; g < groups; g++) {
+            const int nt = p.cm_nt[g], ax = t.x0 + p.cm_dx[g];
+            mbar_wait_t<TIMED>(a_eb, pa, &w_a);
+            if (leader) {
+              mbar_expect_tx_a(a_fb, a_sz);
+              tma_load_5d_a(a_dst, ma, a_fb, kc * 64, ax, 0, ay, t.img);
             }
-            for (int j = 0; j < p.cm_nt[g]; j++) {
-              mbar_wait_t(&empty_bar[sb], pb ^ 1, timed, &w_b);
-              mbar_expect_tx(&full_bar[sb], b_bytes);
-              tma_load_3d(smem_b + (size_t)sb * p.b_slot_bytes, &map_b, &full_bar[sb], kb, n0, p.cm_tap[g][j]);
-              if (++sb == p.b_slots) {
-                sb = 0;
-                pb ^= 1;
+            __syncwarp();
+            a_dst += a_sz; a_fb += 8; a_eb += 8;
+            if (++sa == a_slots) {
+              sa = 0; pa ^= 1; a_dst = smem0; a_fb = afull0; a_eb = aempty0;
+            }
+            for (int j = 0; j < nt; j++) {
+              const int tap = p.cm_tap[g][j];
+              mbar_wait_t<TIMED>(b_eb, pb, &w_b);
+              if (leader) {
+                mbar_expect_tx_a(b_fb, b_bytes);
+                tma_load_3d_a(b_dst, &map_b, b_fb, kb, n0, tap);
+              }
+              __syncwarp();
+              b_dst += b_sz; b_fb += 8; b_eb += 8;
+              if (++sb == b_slots) {
+                sb = 0; pb ^= 1; b_dst = smem_b0; b_fb = full0; b_eb = empty0;
               }
             }
           }
         }
       }
-      if (timed) {
-        long long* o = p.dbg + (size_t)blockIdx.x * 16;
-        o[0] = clock64() - t_start;
-        o[1] = w_a;
-        o[2] = w_b;
-      }
-    } else if (lane == 0) {
+    } else {
+      const int stages = p.stages;
+      const uint32_t st_sz = (uint32_t)p.stage_bytes;
       int stage = 0;
-      uint32_t phase = 0;
-      const bool timed = p.dbg != nullptr;
-      long long w_b = 0;
-      const long long t_start = clock64();
+      uint32_t pe = 1;
+      uint32_t dst = smem0, fb = full0, eb = empty0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int tile = item / nsplit, split = item - tile * nsplit;
-        TileCoord t = decode_tile(p, tile);
+        const TileCoord t = decode_tile(p, tile);
         const int n0 = t.n_tile * p.BN;
         const int k0 = (int)((long long)kiters * split / nsplit), k1 = (int)((long long)kiters * (split + 1) / nsplit);
+        // (tap, chunk) counters advance incrementally: no division in the loop
+        int tap = k0 / nch, c = k0 - tap * nch;
+        int dc = p.tap_dc[tap], ax = t.x0 + p.tap_dx[tap], dp = p.tap_dp[tap], ay = t.y0 + p.tap_dy[tap];
+        int bz = p.w_batched ? t.img : tap;
         for (int ki = k0; ki < k1; ki++) {
-          const KIter k = decode_kiter(p, ki);
-          const CUtensorMap* ma = k.src ? &map_a1 : &map_a0;
-          mbar_wait_t(&empty_bar[stage], phase ^ 1, timed, &w_b);
-          uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-          uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-          tma_load_5d(sa, ma, &full_bar[stage], p.tap_dc[k.tap] + k.kc * 64, t.x0 + p.tap_dx[k.tap], p.tap_dp[k.tap],
-                      t.y0 + p.tap_dy[k.tap], t.img);
-          tma_load_3d(sb, &map_b, &full_bar[stage], (k.src ? p.c1_off : 0) + k.kc * 64, n0,
-                      p.w_batched ? t.img : k.tap);
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
+          const int src = c >= kch0 ? 1 : 0;
+          const int kc = src ? c - kch0 : c;
+          const CUtensorMap* ma = src ? &map_a1 : &map_a0;
+          mbar_wait_t<TIMED>(eb, pe, &w_b);
+          if (leader) {
+            mbar_expect_tx_a(fb, a_bytes + b_bytes);
+            tma_load_5d_a(dst, ma, fb, dc + kc * 64, ax, dp, ay, t.img);
+            tma_load_3d_a(dst + kABytes, &map_b, fb, (src ? c1_off : 0) + kc * 64, n0, bz);
+          }
+          __syncwarp();
+          dst += st_sz; fb += 8; eb += 8;
+          if (++stage == stages) {
+            stage = 0; pe ^= 1; dst = smem0; fb = full0; eb = empty0;
+          }
+          if (++c == nch && ki + 1 < k1) {
+            c = 0;
+            ++tap;
+            dc = p.tap_dc[tap];
+            ax = t.x0 + p.tap_dx[tap];
+            dp = p.tap_dp[tap];
+            ay = t.y0 + p.tap_dy[tap];
+            if (!p.w_batched) bz = tap;
           }
         }
       }
-      if (timed) {
-        long long* o = p.dbg + (size_t)blockIdx.x * 16;
-        o[0] = clock64() - t_start;
-        o[1] = 0;
-        o[2] = w_b;
-      }
+    }
+    if (TIMED && leader) {
+      long long* o = p.dbg + (size_t)blockIdx.x * 16;
+      o[0] = clock64() - t_start;
+      o[1] = w_a;
+      o[2] = w_b;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && !SPLITK && p.colmode) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
+    const uint32_t leader = elect_one();
+    long long w_a = 0, w_b = 0, w_t = 0;
+    const long long t_start = TIMED ? clock64() : 0;
+    const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
+    // descriptor = constant high part | (shared address >> 4): advancing a slot / a row offset / 16 K elements is an add
+    const uint64_t desc_hi = umma_smem_desc(0, 16, 1024);
+    const uint32_t smem_enc = (smem0 & 0x3FFFF) >> 4;
+    int it = 0;
+    if (!SPLITK && p.colmode) {
+      const int nch = p.kchunks[0] + p.kchunks[1], a_slots = p.a_slots, b_slots = p.b_slots, groups = p.cm_groups;
+      const uint32_t a_enc = (uint32_t)p.a_slot_bytes >> 4, b_enc = (uint32_t)p.b_slot_bytes >> 4;
+      const uint32_t smem_b_enc = smem_enc + (uint32_t)a_slots * a_enc;
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      const int nch = p.kchunks[0] + p.kchunks[1];
-      const uint32_t smem_a = smem_u32(smem);
-      const uint32_t smem_b = smem_a + (uint32_t)(p.a_slots * p.a_slot_bytes);
-      const bool timed = p.dbg != nullptr;
-      long long w_a = 0, w_b = 0, w_t = 0;
-      const long long t_start = clock64();
-      int it = 0;
+      uint32_t a_lo = smem_enc, b_lo = smem_b_enc, a_fb = afull0, a_eb = aempty0, b_fb = full0, b_eb = empty0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, it++) {
         const int acc = it & 1;
-        mbar_wait_t(&tmem_empty[acc], ((it >> 1) & 1) ^ 1, timed, &w_t);
+        mbar_wait_t<TIMED>(tempty0 + acc * 8, ((it >> 1) & 1) ^ 1, &w_t);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         uint32_t accumulate = 0;
         for (int c = 0; c < nch; c++) {
-          for (int g = 0; g < p.cm_groups; g++) {
-            mbar_wait_t(&a_full[sa], pa, timed, &w_a);
-            const uint32_t abase = smem_a + (uint32_t)(sa * p.a_slot_bytes);
-            for (int j = 0; j < p.cm_nt[g]; j++) {
-              mbar_wait_t(&full_bar[sb], pb, timed, &w_b);
+          for (int g = 0; g < groups; g++) {
+            const int nt = p.cm_nt[g];
+            mbar_wait_t<TIMED>(a_fb, pa, &w_a);
+            for (int j = 0; j < nt; j++) {
+              const uint32_t row_enc = (uint32_t)p.cm_row[g][j] * 64u;           // rows of 8 pixels x 128 B = 1024 B
+              mbar_wait_t<TIMED>(b_fb, pb, &w_b);
               tc_fence_after();
-              const uint64_t da = umma_smem_desc(abase + (uint32_t)p.cm_row[g][j] * 1024u, 16, 1024);
-              const uint64_t db = umma_smem_desc(smem_b + (uint32_t)(sb * p.b_slot_bytes), 16, 1024);
-#pragma unroll
-              for (int k = 0; k < 4; k++) {
-                umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accumulate);
-                accumulate = 1;
+              if (leader) {
+                const uint64_t da = desc_hi | (uint64_t)(a_lo + row_enc);
+                const uint64_t db = desc_hi | (uint64_t)b_lo;
+                umma_bf16(d_tmem, da, db, idesc, accumulate);
+                umma_bf16(d_tmem, da + 2, db + 2, idesc, 1);
+                umma_bf16(d_tmem, da + 4, db + 4, idesc, 1);
+                umma_bf16(d_tmem, da + 6, db + 6, idesc, 1);
+                umma_commit_a(b_eb);
+                if (j == nt - 1) umma_commit_a(a_eb);         // all taps of this column have read the box
               }
-              umma_commit(&empty_bar[sb]);
-              if (++sb == p.b_slots) {
-                sb = 0;
-                pb ^= 1;
+              __syncwarp();
+              accumulate = 1;
+              b_lo += b_enc; b_fb += 8; b_eb += 8;
+              if (++sb == b_slots) {
+                sb = 0; pb ^= 1; b_lo = smem_b_enc; b_fb = full0; b_eb = empty0;
               }
             }
-            umma_commit(&a_empty[sa]);             // all taps of this column have read the box
-            if (++sa == p.a_slots) {
-              sa = 0;
-              pa ^= 1;
+            a_lo += a_enc; a_fb += 8; a_eb += 8;
+            if (++sa == a_slots) {
+              sa = 0; pa ^= 1; a_lo = smem_enc; a_fb = afull0; a_eb = aempty0;
             }
           }
         }
-        umma_commit(&tmem_full[acc]);
+        if (leader) umma_commit_a(tfull0 + acc * 8);
+        __syncwarp();
       }
-      if (timed) {
-        long long* o = p.dbg + (size_t)blockIdx.x * 16;
-        o[4] = clock64() - t_start;
-        o[5] = w_a;
-        o[6] = w_b;
-        o[7] = w_t;
-      }
-      pdl_trigger();
-    } else if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
+    } else {
+      const int stages = p.stages;
+      const uint32_t stage_enc = (uint32_t)p.stage_bytes >> 4;
       int stage = 0;
       uint32_t phase = 0;
-      const bool timed = p.dbg != nullptr;
-      long long w_b = 0, w_t = 0;
-      const long long t_start = clock64();
-      int it = 0;
+      uint32_t a_lo = smem_enc, fb = full0, eb = empty0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, it++) {
         const int split = item % nsplit;
         const int k0 = (int)((long long)kiters * split / nsplit), k1 = (int)((long long)kiters * (split + 1) / nsplit);
         const int acc = it & 1;
-        mbar_wait_t(&tmem_empty[acc], ((it >> 1) & 1) ^ 1, timed, &w_t);
+        mbar_wait_t<TIMED>(tempty0 + acc * 8, ((it >> 1) & 1) ^ 1, &w_t);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
+        uint32_t accumulate = 0;
         for (int ki = k0; ki < k1; ki++) {
-          mbar_wait_t(&full_bar[stage], phase, timed, &w_b);
+          mbar_wait_t<TIMED>(fb, phase, &w_b);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint64_t da = umma_smem_desc(sa, 16, 1024);
-          const uint64_t db = umma_smem_desc(sa + kABytes, 16, 1024);
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
+          if (leader) {
+            const uint64_t da = desc_hi | (uint64_t)a_lo;
+            const uint64_t db = da + (kABytes >> 4);
             // +32 bytes (16 bf16) along K inside the 128B swizzle atom == +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, ((ki - k0) | k) != 0);
+            umma_bf16(d_tmem, da, db, idesc, accumulate);
+            umma_bf16(d_tmem, da + 2, db + 2, idesc, 1);
+            umma_bf16(d_tmem, da + 4, db + 4, idesc, 1);
+            umma_bf16(d_tmem, da + 6, db + 6, idesc, 1);
+            umma_commit_a(eb);                         // frees the smem slot once these MMAs have read it
           }
-          umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs have read it
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
+          __syncwarp();
+          accumulate = 1;
+          a_lo += stage_enc; fb += 8; eb += 8;
+          if (++stage == stages) {
+            stage = 0; phase ^= 1; a_lo = smem_enc; fb = full0; eb = empty0;
           }
         }
-        umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
+        if (leader) umma_commit_a(tfull0 + acc * 8);   // accumulator complete -> epilogue
+        __syncwarp();
       }
-      if (timed) {
-        long long* o = p.dbg + (size_t)blockIdx.x * 16;
-        o[4] = clock64() - t_start;
-        o[5] = 0;
-        o[6] = w_b;
-        o[7] = w_t;
-      }
-      pdl_trigger();    // this CTA's MMAs are all issued: the next kernel may start its prologue under our epilogue
     }
+    if (TIMED && leader) {
+      long long* o = p.dbg + (size_t)blockIdx.x * 16;
+      o[4] = clock64() - t_start;
+      o[5] = w_a;
+      o[6] = w_b;
+      o[7] = w_t;
+    }
+    if (leader) pdl_trigger();    // this CTA's MMAs are all issued: the next kernel may start under our epilogue
   } else {
     // ===================== epilogue warps =====================
     // warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps of a quarter interleave 32-column chunks.
@@ -621,7 +654,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       // stage this tile's bias slice (GEMM column order) in shared memory
       if (etid < p.BN) bias_s[acc][etid] = (p.bias != nullptr && n0 + etid < p.cout) ? __ldg(p.bias + n0 + etid) : 0.f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (p.dbg != nullptr && threadIdx.x == 64) {
+      if (TIMED && threadIdx.x == 64) {
         const long long t0 = clock64();
         mbar_wait(&tmem_full[acc], (it >> 1) & 1);
         p.dbg[(size_t)blockIdx.x * 16 + 9] += clock64() - t0;
@@ -1262,16 +1295,20 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
                                  : (size_t)p.stages * p.stage_bytes) + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    ONEDC_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ONEDC_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSmemBudget + 1024));
-    ONEDC_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ONEDC_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBudget + 1024));
+    ONEDC_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSmemBudget + 1024));
     attr_set = true;
   }
   if (p.splits > 1)
-    ONEDC_CUDA(launch_k(igemm_tc_kernel<true>, grid, kThreads, smem, stream, ma[0], ma[1], mb, p));
+    ONEDC_CUDA(launch_k(igemm_tc_kernel<true, false>, grid, kThreads, smem, stream, ma[0], ma[1], mb, p));
+  else if (p.dbg != nullptr)
+    ONEDC_CUDA(launch_k(igemm_tc_kernel<false, true>, grid, kThreads, smem, stream, ma[0], ma[1], mb, p));
   else
-    ONEDC_CUDA(launch_k(igemm_tc_kernel<false>, grid, kThreads, smem, stream, ma[0], ma[1], mb, p));
+    ONEDC_CUDA(launch_k(igemm_tc_kernel<false, false>, grid, kThreads, smem, stream, ma[0], ma[1], mb, p));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }
