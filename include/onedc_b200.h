@@ -146,13 +146,14 @@ int64_t onedc_groupnorm_ws_floats(int32_t n_img, int64_t hw, int32_t c_total);
 int onedc_groupnorm_stats(const void* x0, int32_t c0, int64_t ld0, const void* x1, int32_t c1, int64_t ld1,
                           int32_t in_dtype, int32_t n_img, int64_t hw, int32_t groups, float eps, float* partial,
                           float* stats, uint32_t* counters, const int32_t* valid_px, void* stream);
-/* statistics come either from `stats` (onedc_groupnorm_stats) or, when acc0 != NULL (single source only), from the
- * per-group fp64 (sum, sum of squares) accumulators [n_img][groups][2] that onedc_igemm fused into the producer's
- * epilogue; acc1 is reserved */
+/* statistics come either from `stats` (onedc_groupnorm_stats) or, when acc0 != NULL, from the fp64 (sum, sum of
+ * squares) accumulators that onedc_igemm fused into the producers' epilogues: per group [n_img][groups][2] (single
+ * source, acc_per_channel = 0) or per channel [n_img][c0][2] / [n_img][c1][2] (acc_per_channel = 1; acc1 belongs to
+ * the second source of a concatenation) */
 int onedc_groupnorm_apply(const void* x0, int32_t c0, int64_t ld0, const void* x1, int32_t c1, int64_t ld1,
                           int32_t in_dtype, int32_t n_img, int64_t hw, int32_t groups, const float* stats,
-                          const double* acc0, const double* acc1, float eps, const float* gamma, const float* beta,
-                          int32_t silu, void* out, int64_t out_ld, void* stream);
+                          const double* acc0, const double* acc1, int32_t acc_per_channel, float eps,
+                          const float* gamma, const float* beta, int32_t silu, void* out, int64_t out_ld, void* stream);
 int onedc_layernorm(const void* x, int64_t ld, int64_t rows, int32_t c, const float* gamma, const float* beta,
                     float eps, void* out, int64_t out_ld, void* stream);
 /* scores fp32 [rows, ld] -> bf16 probabilities [rows, out_ld]; columns >= valid are written as 0 */

@@ -68,7 +68,8 @@ struct IgemmParams {
   int vec_ok;
   // split-K (small-M layers): fp32 partial tiles + per-tile arrival counters
   double* gn_acc;         // optional per-GROUP (sum, sum of squares) of the stored outputs, [img][gn_groups][2]
-  int gn_ng, gn_groups;   // groups per 32-column chunk (8/4/2/1, i.e. 4/8/16/32 channels per group), groups per image
+  int gn_ng, gn_groups;   // groups per 32-column chunk (32/8/4/2/1, i.e. 1/4/8/16/32 channels per group), groups per
+                          // image; 1 channel per group = per-CHANNEL sums, regrouped by the consuming GroupNorm
   int splits;
   float* ws;
   int* counters;
@@ -748,6 +749,29 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             epi_finish32<true>(p, a, b, &bias_s[acc][c], &bias_s[acc][half + c], vld, t.img, yy, xx, pix2, o0 + c);
           else
             epi_finish32<false>(p, a, a, &bias_s[acc][c], &bias_s[acc][c], vld, t.img, yy, xx, pix2, o0 + c);
+          if (p.gn_acc != nullptr) {
+            // fused GroupNorm statistics: park the finished values (zeros for padding rows) where the accumulators were
+            float4* wr = reinterpret_cast<float4*>(red + (size_t)rl * p.BN + c);
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+              wr[i] = vld ? make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (p.gn_acc != nullptr) {
+          // one thread per output column sums this CTA's row slice in a fixed order, then one fp64 atomic pair
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const int cpg = p.cout / p.gn_groups;
+          for (int col = etid; col < out_cols_tile; col += 256) {
+            float s1 = 0.f, s2 = 0.f;                   // <= 32 rows: fp32 is plenty, the cross-CTA sum is fp64
+            for (int rr = 0; rr < r1 - r0; rr++) {
+              const float xv = red[(size_t)rr * p.BN + col];
+              s1 += xv;
+              s2 += xv * xv;
+            }
+            double* dst = p.gn_acc + ((size_t)t.img * p.gn_groups + (o0 + col) / cpg) * 2;
+            atomicAdd(dst, (double)s1);
+            atomicAdd(dst + 1, (double)s2);
+          }
         }
         // last CTA to finish re-arms the counters (nobody can still be spinning: all have passed the wait)
         asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -804,7 +828,8 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             // GroupNorm statistics of what was just stored: per-group sums over this warp's 32 rows, kept in
             // registers across the CTA's tiles, flushed with one fp64 atomic per group when the tile column changes
             float s1, s2;
-            if (p.gn_ng == 8) chunk_group_stats<8>(a, valid, lane, &s1, &s2);
+            if (p.gn_ng == 32) chunk_group_stats<32>(a, valid, lane, &s1, &s2);      // per channel
+            else if (p.gn_ng == 8) chunk_group_stats<8>(a, valid, lane, &s1, &s2);
             else if (p.gn_ng == 4) chunk_group_stats<4>(a, valid, lane, &s1, &s2);
             else if (p.gn_ng == 2) chunk_group_stats<2>(a, valid, lane, &s1, &s2);
             else chunk_group_stats<1>(a, valid, lane, &s1, &s2);
@@ -1204,7 +1229,10 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
         p.a_slots = p.BN <= 128 ? 4 : 3;
         p.b_slots = (kSmemBudget - p.a_slots * p.a_slot_bytes) / p.b_slot_bytes;
         if (p.b_slots > kMaxStages) p.b_slots = kMaxStages;
-        if (p.b_slots >= 3) {
+        // measured on B200: wins 4-6 % when a CTA runs several tiles back to back, loses on single-wave layers
+        const int tiles16x8 = p.n_img * ((p.H + 15) / 16) * ((p.W + 7) / 8) * p.n_tiles;
+        static const bool colmode_all = getenv("ONEDC_COLMODE") != nullptr && getenv("ONEDC_COLMODE")[0] == '2';
+        if (p.b_slots >= 3 && (colmode_all || tiles16x8 > sm_count())) {
           p.colmode = 1;
           p.TH = 16;
           p.TW = 8;
@@ -1219,11 +1247,11 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
   p.dbg = g_igemm_dbg;
   p.gn_acc = nullptr;
   d->gn_fused_out = 0;
-  if (d->gn_acc != nullptr && d->impl != 1 && !pair && p.splits == 1) {
+  if (d->gn_acc != nullptr && d->impl != 1 && !pair) {
     const bool fast_all = p.vec_ok && (d->cout % p.BN == 0) && (p.BN % 32 == 0) &&
                           (d->store_mode == ST_NORMAL || d->store_mode == ST_QUAD) && p.BN <= 256;
     const int cpg = d->gn_groups > 0 ? d->cout / d->gn_groups : 0;
-    if (fast_all && d->gn_groups > 0 && d->cout % d->gn_groups == 0 && (cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32)) {
+    if (fast_all && d->gn_groups > 0 && d->cout % d->gn_groups == 0 && (cpg == 1 || cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32)) {
       p.gn_acc = reinterpret_cast<double*>(d->gn_acc);
       p.gn_ng = 32 / cpg;
       p.gn_groups = d->gn_groups;

@@ -206,9 +206,9 @@ __global__ void __launch_bounds__(256, 4) gn_stats_kernel(GnSrc s, long long hw,
 
 template <int VX>
 __global__ void __launch_bounds__(256, 4) gn_apply_kernel(GnSrc s, long long hw, int groups, const float* stats,
-                                                       const double* acc0, const double* acc1, float eps,
-                                                       const float* gamma, const float* beta, int silu, void* out,
-                                                       long long out_ld, int px_per_block) {
+                                                       const double* acc0, const double* acc1, int acc_per_channel,
+                                                       float eps, const float* gamma, const float* beta, int silu,
+                                                       void* out, long long out_ld, int px_per_block) {
   pdl_wait();
   constexpr int PY = 256 / VX;
   const int tx = threadIdx.x % VX, ty = threadIdx.x / VX;
@@ -217,7 +217,35 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(GnSrc s, long long hw,
   const int n = blockIdx.z;
   const int cpg = C / groups;
   __shared__ float gstat[64][2];
-  if (acc0 != nullptr) {
+  if (acc0 != nullptr && acc_per_channel) {
+    // statistics were accumulated per CHANNEL by the producing igemm epilogues (one accumulator per source, so a
+    // channel concatenation needs nothing extra): 8 threads fold the channels of one group, 32 groups per pass
+    for (int gb = 0; gb < groups; gb += 32) {
+      const int g = gb + ((int)threadIdx.x >> 3), sub = threadIdx.x & 7;
+      double a = 0.0, b = 0.0;
+      if (g < groups) {
+        for (int c = g * cpg + sub; c < (g + 1) * cpg; c += 8) {
+          const double* src = c < s.c0 ? acc0 + ((size_t)n * s.c0 + c) * 2 : acc1 + ((size_t)n * s.c1 + (c - s.c0)) * 2;
+          a += __ldcg(src);
+          b += __ldcg(src + 1);
+        }
+      }
+#pragma unroll
+      for (int o = 4; o >= 1; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (sub == 0 && g < groups) {
+        const double cnt = (double)hw * cpg;
+        const double mean = a / cnt;
+        double var = b / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        gstat[g][0] = (float)mean;
+        gstat[g][1] = (float)(1.0 / sqrt(var + (double)eps));
+      }
+    }
+    __syncthreads();
+  } else if (acc0 != nullptr) {
     // statistics were accumulated per group by the producing igemm epilogue(s) (single source only)
     if ((int)threadIdx.x < groups) {
       const int g = threadIdx.x;
@@ -419,9 +447,11 @@ extern "C" int onedc_groupnorm_stats(const void* x0, int32_t c0, int64_t ld0, co
 
 extern "C" int onedc_groupnorm_apply(const void* x0, int32_t c0, int64_t ld0, const void* x1, int32_t c1, int64_t ld1,
                                      int32_t in_dtype, int32_t n_img, int64_t hw, int32_t groups, const float* stats,
-                                     const double* acc0, const double* acc1, float eps, const float* gamma,
-                                     const float* beta, int32_t silu, void* out, int64_t out_ld, void* stream) {
-  ONEDC_CHECK(stats != nullptr || (acc0 != nullptr && c1 == 0), "groupnorm_apply: no statistics");
+                                     const double* acc0, const double* acc1, int32_t acc_per_channel, float eps,
+                                     const float* gamma, const float* beta, int32_t silu, void* out, int64_t out_ld,
+                                     void* stream) {
+  ONEDC_CHECK(stats != nullptr || (acc0 != nullptr && (c1 == 0 || (acc_per_channel && acc1 != nullptr))),
+              "groupnorm_apply: no statistics");
   const int C = c0 + c1;
   ONEDC_CHECK(c0 % 8 == 0 && c1 % 8 == 0 && C % groups == 0 && out_ld % 8 == 0, "groupnorm: bad channels");
   GnSrc s{x0, x1, c0, c1, ld0, ld1, in_dtype};
@@ -431,10 +461,10 @@ extern "C" int onedc_groupnorm_apply(const void* x0, int32_t c0, int64_t ld0, co
   ONEDC_CHECK(chunks <= 65535 && n_img <= 65535, "groupnorm: grid too large");
   if (nvec <= 16) {
     dim3 grid((nvec + 15) / 16, chunks, n_img);
-    ONEDC_CUDA(launch_k(gn_apply_kernel<16>, grid, 256, 0, (cudaStream_t)stream, s, hw, groups, stats, acc0, acc1, eps, gamma, beta, silu, out, out_ld, px));
+    ONEDC_CUDA(launch_k(gn_apply_kernel<16>, grid, 256, 0, (cudaStream_t)stream, s, hw, groups, stats, acc0, acc1, acc_per_channel, eps, gamma, beta, silu, out, out_ld, px));
   } else {
     dim3 grid((nvec + 31) / 32, chunks, n_img);
-    ONEDC_CUDA(launch_k(gn_apply_kernel<32>, grid, 256, 0, (cudaStream_t)stream, s, hw, groups, stats, acc0, acc1, eps, gamma, beta, silu, out, out_ld, px));
+    ONEDC_CUDA(launch_k(gn_apply_kernel<32>, grid, 256, 0, (cudaStream_t)stream, s, hw, groups, stats, acc0, acc1, acc_per_channel, eps, gamma, beta, silu, out, out_ld, px));
   }
   ONEDC_CUDA(cudaGetLastError());
   return 0;

@@ -46,7 +46,7 @@ PROTOTYPES = {
     "onedc_attention": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
     "onedc_groupnorm_ws_floats": (_i64, [_i32, _i64, _i32]),
     "onedc_groupnorm_stats": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
-    "onedc_groupnorm_apply": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _f32,
+    "onedc_groupnorm_apply": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _i32, _f32,
                                         _vp, _vp, _i32, _vp, _i64, _vp]),
     "onedc_layernorm": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _i64, _vp]),
     "onedc_softmax_rows": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _f32, _vp, _i64, _vp]),

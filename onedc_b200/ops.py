@@ -229,10 +229,14 @@ def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None
         d.splitk_ws, d.splitk_ws_floats, d.splitk_counters, d.splitk_max_tiles = ws.data_ptr(), ws.numel(), cnt.data_ptr(), cnt.numel()
     acc = None
     if stats is not False and GN_FUSED and d.impl == 0:
-        # stats=True: new accumulator slice; stats=<tensor>: keep accumulating into it (the 4 phases of an UpConv)
-        acc = _gn_arena_alloc(x.device, n * 32 * 2) if stats is True else stats
+        # stats=True: new accumulator slice; stats=<tensor>: keep accumulating into it (the 4 phases of an UpConv).
+        # Per-GROUP sums when a 32-column chunk holds whole groups (4/8/16/32 channels per group), else per-CHANNEL
+        # sums (UNet widths 320/640/1280: 10/20/40 channels per group), which also serve channel concatenations.
+        per_group = (d.cout % 32 == 0) and (d.cout // 32) in (4, 8, 16, 32)
+        ngrp = 32 if per_group else d.cout
+        acc = _gn_arena_alloc(x.device, n * ngrp * 2) if stats is True else stats
         if acc is not None:
-            d.gn_acc, d.gn_groups = acc.data_ptr(), 32
+            d.gn_acc, d.gn_groups = acc.data_ptr(), ngrp
     if PROFILE is not None:
         taps_ = d.ntaps if d.ntaps > 0 else d.ksize * d.ksize
         abytes = 2.0 * n * h * w * (c0 + c1) + 2.0 * d.cout * d.ktot * taps_ + out.element_size() * float(n * ho * wo * ncols) \
@@ -248,6 +252,7 @@ def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None
     _prof_end("igemm", e0, 2.0 * n * ho * wo * d.cout * (c0 + c1) * (d.ntaps if d.ntaps > 0 else d.ksize * d.ksize))
     if acc is not None and d.gn_fused_out:
         out._gn_acc = acc
+        out._gn_chan = d.gn_groups != 32
     elif hasattr(out, "_gn_acc"):
         del out._gn_acc
     return out
@@ -352,8 +357,13 @@ class GroupNorm:
             p1, _, _, _, c1, s1 = _nhwc(x2)
         hw, ct = h * w, c0 + c1
         assert n <= 8192
-        a0 = getattr(x, "_gn_acc", None) if (GN_FUSED and valid is None and x2 is None and self.groups == 32) else None
-        a1 = None
+        a0 = getattr(x, "_gn_acc", None) if (GN_FUSED and valid is None and self.groups == 32) else None
+        a1 = getattr(x2, "_gn_acc", None) if (a0 is not None and x2 is not None) else None
+        chan = bool(a0 is not None and getattr(x, "_gn_chan", False))
+        if a0 is not None and x2 is not None:
+            # a concatenation needs per-channel sums of BOTH sources
+            if a1 is None or not chan or not getattr(x2, "_gn_chan", False):
+                a0 = a1 = None
         fused = a0 is not None
         stats_ptr = 0
         if not fused:
@@ -369,7 +379,7 @@ class GroupNorm:
         po, _, _, _, _, so = _nhwc(out)
         L.check(lib.onedc_groupnorm_apply(p0, c0, s0, p1, c1, s1, _dt(x), n, hw, self.groups, stats_ptr,
                                           a0.data_ptr() if fused else 0, a1.data_ptr() if (fused and a1 is not None) else 0,
-                                          self.eps, self.gamma.data_ptr(), self.beta.data_ptr(), 1 if silu else 0, po, so,
+                                          1 if (fused and chan) else 0, self.eps, self.gamma.data_ptr(), self.beta.data_ptr(), 1 if silu else 0, po, so,
                                           _stream()), "groupnorm_apply")
         return out
 

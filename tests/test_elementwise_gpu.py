@@ -179,7 +179,8 @@ def test_quantize_residual_roundtrip(cuda):
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout,two", [(1, 32, 32, 128, 128, False), (2, 64, 48, 128, 256, False), (1, 96, 96, 64, 512, False),
-                                                (1, 24, 24, 256, 320, True)])
+                                                (1, 24, 24, 256, 320, True), (2, 96, 96, 64, 320, False), (1, 48, 48, 128, 640, True),
+                                                (1, 40, 24, 64, 1280, False), (1, 24, 24, 1280, 1280, False), (1, 12, 12, 1280, 512, True)])
 def test_groupnorm_statistics_fused_into_igemm(cuda, n, h, w, cin, cout, two):
     """conv -> GroupNorm with the statistics accumulated by the conv's epilogue == the two-kernel GroupNorm."""
     from onedc_b200 import ops
@@ -188,7 +189,12 @@ def test_groupnorm_statistics_fused_into_igemm(cuda, n, h, w, cin, cout, two):
     wt = torch.randn((cout, cin, 3, 3), generator=torch.Generator().manual_seed(2)) * (cin * 9) ** -0.5
     cw = ops.ConvW(wt, torch.randn(cout, generator=torch.Generator().manual_seed(3)) * 0.3, cuda)
     y = ops.igemm(x, cw, stats=True)
-    assert hasattr(y, "_gn_acc") == (not two), "fusion applies to 4/8/16/32 channels per group, single source"
+    # 4/8/16/32 channels per group: per-group sums; other widths (UNet: 10/20/40): per-channel sums, which also cover
+    # channel concatenations.  Layers that split K (few tiles, long K) leave the statistics to the GroupNorm kernel.
+    if cout % 32 == 0 and cout // 32 in (4, 8, 16, 32):
+        assert hasattr(y, "_gn_acc") and not y._gn_chan
+    elif hasattr(y, "_gn_acc"):
+        assert y._gn_chan
     y2 = ops.igemm(x, cw, stats=True) if two else None
     c = cout * (2 if two else 1)
     g = torch.Generator().manual_seed(4)
@@ -198,4 +204,4 @@ def test_groupnorm_statistics_fused_into_igemm(cuda, n, h, w, cin, cout, two):
     ys = y.float() if y2 is None else torch.cat([y.float(), y2.float()], -1)
     ref = F.silu(F.group_norm(ys.permute(0, 3, 1, 2), 32, gn.gamma, gn.beta, 1e-5)).permute(0, 2, 3, 1)
     assert (fused.float() - ref).abs().max().item() < 3e-2
-    assert (fused.float() - plain.float()).abs().max().item() < 2e-2
+    assert (fused.float() - plain.float()).abs().max().item() < 4e-2          # one bf16 ulp at |y| >= 4

@@ -220,7 +220,8 @@ def test_column_copy_mode_3x3(cuda, n, h, w, cin, cin2, cout):
     acc = getattr(out, "_gn_acc", None)
     if acc is not None:                          # fused statistics: per (image, group) sum and sum of squares
         torch.cuda.synchronize()
-        got = acc[: n * 32 * 2].view(n, 32, 2)
-        o = out.float().view(n, h * w, 32, cout // 32)
+        ng = cout if out._gn_chan else 32
+        got = acc[: n * ng * 2].view(n, ng, 2)
+        o = out.float().view(n, h * w, ng, cout // ng)
         want = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1).double()
         assert torch.allclose(got, want, rtol=2e-3, atol=1e-2 * float(want.abs().max()) * 1e-2)

@@ -178,7 +178,7 @@ def test_sizes_with_edge_windows_and_padding(bundle, hh, ww):
     print(f"{hh}x{ww}: PSNR vs oracle generator {p:.2f} dB")
     assert p >= 45.0
     g = model.decode(stream=stream)                       # graph route
-    assert _psnr01(g.cpu(), img.cpu()) > 55 and torch.equal(g, model.decode(stream=stream))
+    assert _psnr01(g.cpu(), img.cpu()) > 52 and torch.equal(g, model.decode(stream=stream))
 
 
 def test_programmatic_dependent_launch_is_bit_identical(bundle):
