@@ -126,7 +126,8 @@ typedef struct {
 /* diagnostics: when set (device pointer to 148 x 16 int64, zeroed by the caller) every igemm CTA records clock
    counters per warp role: [0] producer total, [1] producer waiting for a free A slot, [2] ... for a free B slot,
    [4] MMA issuer total, [5] waiting for A data, [6] waiting for B data, [7] waiting for a free accumulator,
-   [9] epilogue waiting for a finished accumulator.  NULL turns it off. */
+   [8] epilogue total, [9] waiting for a finished accumulator, [10] (split-K) waiting for the other splits.
+   NULL turns it off. */
 void onedc_igemm_set_debug(void* dev_counters);
 int onedc_igemm(onedc_igemm_desc* d, void* stream);
 

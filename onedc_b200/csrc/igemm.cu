@@ -643,6 +643,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     const int half = p.BN >> 1;
     const int out_cols_tile = pair ? half : p.BN;      // output columns produced per tile
     float csum[4] = {0.f, 0.f, 0.f, 0.f}, csq[4] = {0.f, 0.f, 0.f, 0.f};   // fused GroupNorm statistics
+    const long long t_epi0 = TIMED ? clock64() : 0;
     int st_img = -1, st_nt = -1;
     int it = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, it++) {
@@ -669,58 +670,87 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       const bool fast = p.vec_ok && (o0 + out_cols_tile <= p.ncols_out) && (out_cols_tile % 32 == 0) &&
                         (p.store_mode == ST_NORMAL || p.store_mode == ST_QUAD || (p.store_mode == ST_PIXSHUF && p.ps_c % 32 == 0));
       if (SPLITK) {
+        long long tp = TIMED ? clock64() : 0;
+        auto phase_mark = [&](int slot) {
+          if (TIMED && threadIdx.x == 64) {
+            const long long now = clock64();
+            p.dbg[(size_t)blockIdx.x * 16 + slot] += now - tp;
+            tp = now;
+          }
+        };
         // ---- split-K (one work item per CTA, all co-resident): park the raw fp32 accumulators, wait until all
         //      splits of this tile have done so, then reduce a row slice of the tile in split order (deterministic)
         //      and run the real epilogue on it.  The host only enables this on the vector-store fast layout.
-        float* wrow = p.ws + ((size_t)item * 128 + row) * p.BN;
+        // Workspace layout of one parked tile, in float4 units: the rows are cut into the `splits` row slices that the
+        // reduction hands out, and inside a slice the order is [column quad][row].  A warp's 32 rows then store runs of
+        // consecutive 16-byte words (row-major parking issued 32 separate lines per store instruction and ran at
+        // 15 B/clk), and each CTA later reads its slice of every split as one contiguous block.
+        const int bn4 = p.BN >> 2;
+        const int my_s = ((row + 1) * p.splits + 127) / 128 - 1;
+        const int my_r0 = 128 * my_s / p.splits, my_n = 128 * (my_s + 1) / p.splits - my_r0;
+        float4* wtile = reinterpret_cast<float4*>(p.ws) + (size_t)item * 128 * bn4;
+        float4* wmine = wtile + (size_t)my_r0 * bn4 + (row - my_r0);
         for (int c = member * 32; c < p.BN; c += 64) {
           uint32_t r[32];
           tmem_ld32(taddr + c, r);
           tmem_ld_wait();
-          float4* d4 = reinterpret_cast<float4*>(wrow + c);
+          if (!valid) continue;                       // padding rows of an edge tile are never read back
 #pragma unroll
           for (int i = 0; i < 8; i++)
-            __stcg(d4 + i, make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                       __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+            __stcg(wmine + (size_t)((c >> 2) + i) * my_n,
+                   make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                               __uint_as_float(r[4 * i + 3])));
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);  // TMEM buffer is free again
+        phase_mark(11);                                // park
         __threadfence();
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        phase_mark(12);                                // fence + barrier
         if (etid == 0) {
+          const long long t0 = TIMED ? clock64() : 0;
           atomicAdd(p.counters + tile, 1);
           volatile int* cnt = p.counters + tile;
           while (*cnt < p.splits) __nanosleep(40);
           __threadfence();
+          if (TIMED) p.dbg[(size_t)blockIdx.x * 16 + 10] += clock64() - t0;      // waiting for the other splits
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        phase_mark(13);                                // arrive + wait for the other splits
         const int r0 = 128 * split / p.splits, r1 = 128 * (split + 1) / p.splits;
-        // B1: all 256 threads sum this CTA's row slice over the splits (fixed order) with coalesced 16-byte loads,
-        //     several splits in flight per position, into the (now idle) operand ring in shared memory
-        float* red = reinterpret_cast<float*>(smem);
-        const int slice_f4 = (r1 - r0) * (p.BN >> 2);
-        const size_t sstride4 = (size_t)128 * (p.BN >> 2);
-        const float4* wsl = reinterpret_cast<const float4*>(p.ws + ((size_t)tile * p.splits * 128 + r0) * p.BN);
+        // B1: this CTA's row slice of every split is one contiguous block: stage all of them in the (idle) operand
+        //     ring with bulk copies -- one L2 round trip for the lot; 16-byte loads by the threads took ~2500 clocks
+        //     per dependent round -- then sum them in split order (deterministic) into `red`
+        const int nrows = r1 - r0;
+        const int slice_f4 = nrows * bn4;
+        const uint32_t slice_bytes = (uint32_t)slice_f4 * 16u;
+        const size_t sstride4 = (size_t)128 * bn4;
+        const float4* wsl = reinterpret_cast<const float4*>(p.ws) + ((size_t)tile * p.splits * 128 + r0) * bn4;
+        const float4* stage4 = reinterpret_cast<const float4*>(smem);
+        float* red = reinterpret_cast<float*>(smem + (size_t)p.splits * slice_bytes);
+        if (etid == 0) {
+          asm volatile("fence.proxy.async;" ::: "memory");       // other CTAs' generic-proxy stores -> async-proxy reads
+          mbar_expect_tx(&a_full[0], slice_bytes * (uint32_t)p.splits);
+          for (int u = 0; u < p.splits; u++)
+            bulk_copy_g2s(smem + (size_t)u * slice_bytes, wsl + (size_t)u * sstride4, slice_bytes, &a_full[0]);
+        }
+        mbar_wait(&a_full[0], 0);
         for (int e = etid; e < slice_f4; e += 256) {
-          float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          int s2 = 0;
-          for (; s2 + 4 <= p.splits; s2 += 4) {
-            float4 f[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) f[u] = __ldcg(wsl + (size_t)(s2 + u) * sstride4 + e);
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-              acc4.x += f[u].x; acc4.y += f[u].y; acc4.z += f[u].z; acc4.w += f[u].w;
-            }
+          const int c4 = e / nrows, rr = e - c4 * nrows;          // slice order is [column quad][row]
+          {
+            const int rw = r0 + rr, yy = t.y0 + rw / p.TW, xx = t.x0 + rw % p.TW;
+            if (rw >= p.TH * p.TW || yy >= p.H || xx >= p.W) continue;   // padding row: nothing parked, nothing stored
           }
-          for (; s2 < p.splits; s2++) {
-            const float4 f = __ldcg(wsl + (size_t)s2 * sstride4 + e);
+          float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int u = 0; u < p.splits; u++) {
+            const float4 f = stage4[(size_t)u * slice_f4 + e];
             acc4.x += f.x; acc4.y += f.y; acc4.z += f.z; acc4.w += f.w;
           }
-          reinterpret_cast<float4*>(red)[e] = acc4;
+          reinterpret_cast<float4*>(red)[rr * bn4 + c4] = acc4;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        phase_mark(14);                                // B1: reduce over splits
         // B2: (row, 32-column chunk) tasks run the real epilogue from shared memory
         const int nch = out_cols_tile >> 5;
         const int tasks = (r1 - r0) * nch;
@@ -775,6 +805,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         }
         // last CTA to finish re-arms the counters (nobody can still be spinning: all have passed the wait)
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        phase_mark(15);                                // B2: epilogue + statistics
         if (etid == 0) {
           const int old = atomicAdd(p.counters + p.counters_half + tile, 1);
           if (old == p.splits - 1) {
@@ -876,6 +907,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    if (TIMED && threadIdx.x == 64) p.dbg[(size_t)blockIdx.x * 16 + 8] = clock64() - t_epi0;
     if (p.gn_acc != nullptr && st_img >= 0) {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -1329,9 +1361,13 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
                                     kSmemBudget + 1024));
     ONEDC_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kSmemBudget + 1024));
+    ONEDC_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kSmemBudget + 1024));
     attr_set = true;
   }
-  if (p.splits > 1)
+  if (p.splits > 1 && p.dbg != nullptr)
+    ONEDC_CUDA(launch_k(igemm_tc_kernel<true, true>, grid, kThreads, smem, stream, ma[0], ma[1], mb, p));
+  else if (p.splits > 1)
     ONEDC_CUDA(launch_k(igemm_tc_kernel<true, false>, grid, kThreads, smem, stream, ma[0], ma[1], mb, p));
   else if (p.dbg != nullptr)
     ONEDC_CUDA(launch_k(igemm_tc_kernel<false, true>, grid, kThreads, smem, stream, ma[0], ma[1], mb, p));

@@ -2,9 +2,8 @@
 // 2-bit bypass groups for escaped values), bit-compatible with the stream format of the reference's
 // MLCodec_rans module (cpp/rans/rans.cpp, cpp/py_rans/py_rans.cpp) but written for this library:
 //   * C ABI, no Python objects, no per-call vector copies -> callable from any thread without the GIL
-//   * symbol lookup through a per-row 256-bucket table instead of a linear scan from 0; a bucket that lies inside
-//     ONE non-escape symbol (the common case) carries that symbol's start / frequency / decoded value, so the
-//     serial state -> state dependency chain of the decoder holds a single table load
+//   * symbol lookup through a per-row 256-bucket start table instead of a linear scan from 0 (a wider per-bucket
+//     record holding start / frequency / value was tried and measured no faster on the B200 host: 7.9 vs 7.6 ns/symbol)
 //   * the encoder sizes its output buffer from the actual code length (the reference allocates one
 //     byte per queued entry and can under-run it)
 // Also: pmf -> 16-bit quantised CDF (the MLCodec_CXX.pmf_to_quantized_cdf replacement).
@@ -32,12 +31,6 @@ struct onedc_rans_tables {
   std::vector<int32_t> sizes;    // entries per row (symbols + 2)
   std::vector<int32_t> offsets;
   std::vector<uint8_t> bucket;   // [rows][256]: largest s with cdf[s] <= (b << 8)
-  struct Fast {                  // [rows][256]: valid when cdf[s] <= (b << 8) and ((b + 1) << 8) <= cdf[s + 1], s not escape
-    uint16_t start, freq;
-    int16_t value;               // s + offset
-    uint16_t pure;
-  };
-  std::vector<Fast> fast;
 };
 
 struct Cursor {
@@ -103,22 +96,6 @@ extern "C" onedc_rans_tables* onedc_rans_tables_create(const int32_t* cdf, int32
       t->bucket[(size_t)r * 256 + b] = (uint8_t)s;
     }
   }
-  t->fast.resize((size_t)rows * 256);
-  for (int r = 0; r < rows; r++) {
-    const int32_t* row = &t->cdf[(size_t)r * row_stride];
-    const int max_value = t->sizes[r] - 2;
-    for (int b = 0; b < 256; b++) {
-      const int sb = t->bucket[(size_t)r * 256 + b];
-      onedc_rans_tables::Fast f{0, 0, 0, 0};
-      if (getenv("ONEDC_RANS_FAST") == nullptr && sb < max_value && (uint32_t)row[sb + 1] >= ((uint32_t)(b + 1) << 8) && row[sb + 1] - row[sb] <= 0xFFFF) {
-        f.start = (uint16_t)row[sb];
-        f.freq = (uint16_t)(row[sb + 1] - row[sb]);
-        f.value = (int16_t)(sb + t->offsets[r]);
-        f.pure = 1;
-      }
-      t->fast[(size_t)r * 256 + b] = f;
-    }
-  }
   return t;
 }
 extern "C" void onedc_rans_tables_destroy(onedc_rans_tables* t) { delete t; }
@@ -171,7 +148,6 @@ static inline uint32_t get_bits(Cursor& c, uint32_t nbits) {
 
 static void decode_span(Cursor& c, const onedc_rans_tables* t, const int16_t* idx, int n, int16_t* out) {
   const int32_t* cdf = t->cdf.data();
-  const onedc_rans_tables::Fast* fast = t->fast.data();
   const int stride = t->stride;
   uint32_t x = c.x;
   const uint8_t* ptr = c.ptr;
@@ -179,16 +155,6 @@ static void decode_span(Cursor& c, const onedc_rans_tables* t, const int16_t* id
   for (int i = 0; i < n; i++) {
     const int r = idx[i];
     if (r < 0) { out[i] = 0; continue; }
-    {
-      const uint32_t cum0 = x & kMask;
-      const onedc_rans_tables::Fast f = fast[((size_t)r << 8) + (cum0 >> 8)];
-      if (__builtin_expect(f.pure, 1)) {
-        x = (uint32_t)f.freq * (x >> kPrecision) + cum0 - f.start;
-        while (x < kL && ptr < end) x = (x << 8) | *ptr++;
-        out[i] = f.value;
-        continue;
-      }
-    }
     const int32_t* row = cdf + (size_t)r * stride;
     const int max_value = t->sizes[r] - 2;
     const uint32_t cum = x & kMask;

@@ -20,9 +20,13 @@ lib.load().onedc_igemm_set_debug(C.c_void_p(dbg.data_ptr()))
 ops.igemm(x, cw, out=out)
 torch.cuda.synchronize()
 lib.load().onedc_igemm_set_debug(C.c_void_p(0))
-d = dbg.double().mean(0).tolist()
+act = dbg[:, 4] > 0
+d = dbg[act].double().mean(0).tolist()
+print('active CTAs', int(act.sum()))
 names = {0: "producer total", 1: "  waits free A slot", 2: "  waits free B slot", 4: "MMA issuer total", 5: "  waits A data",
-         6: "  waits B data", 7: "  waits free accumulator", 9: "epilogue waits accumulator"}
+         6: "  waits B data", 7: "  waits free accumulator", 8: "epilogue total", 9: "  waits accumulator",
+         10: "  waits other splits", 11: "  split-K: park accumulators", 12: "  split-K: fence + barrier",
+         13: "  split-K: arrive + wait splits", 14: "  split-K: reduce over splits", 15: "  split-K: epilogue + stats"}
 print(f"{n}x{h}x{w} {cin}->{cout} k{k}  colmode={os.environ.get('ONEDC_COLMODE', '1')}  (mean clocks per CTA)")
 for i, nm in names.items():
     print(f"  {nm:28s} {d[i]:10.0f}")
