@@ -78,20 +78,39 @@ def _state_dicts():
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def run_reference(args):
-    """The reference's CPU implementation of the path: the oracle port (kind "port": the reference's UNet/VAE live
-    in diffusers/peft which are not installable here, so the reference itself cannot run), fp32, all host threads.
-    Each step decodes one bounded-size synthetic image; MP/s is size-normalised."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def _oracle_and_size(args, budget_s):
+    """Builds the CPU oracle and picks the largest square sample (768 = the workload itself, else 512 / 256) whose
+    `budget_s` seconds of decodes fit; decode time scales with the pixel count."""
     import torch
     from oracle.decode import OneDCOracle
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    side = args.ref_size
     sds = _state_dicts()
     orc = OneDCOracle(sds[1], sds[0], sds[2])
+    s256, _, _ = orc.codec.make_stream(256, 256, seed=1234)
+    orc.decode(s256)                                   # warm-up (thread pools, allocator)
+    t0 = time.perf_counter()
+    orc.decode(s256)
+    t256 = time.perf_counter() - t0
+    side = args.ref_size
+    if side <= 0:
+        side = 256
+        for cand in (768, 512):
+            if t256 * (cand / 256.0) ** 2 * budget_s[0] <= budget_s[1]:
+                side = cand
+                break
+    return orc, cores, side, t256
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path: the oracle port (kind "port": the reference's UNet/VAE live
+    in diffusers/peft which are not installable here, so the reference itself cannot run), fp32, all host threads.
+    Each step decodes one synthetic image of the workload's size when K + W such decodes fit ~2.5 minutes, else a
+    smaller bounded sample; MP/s is size-normalised."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    orc, cores, side, t256 = _oracle_and_size(args, (args.steps + args.warmup, 150.0))
     stream, _, _ = orc.codec.make_stream(side, side, seed=1234)
     for _ in range(args.warmup):
         orc.decode(stream)
@@ -105,8 +124,9 @@ def run_reference(args):
         "impl": "reference", "metric": "768x768 decode throughput", "value": v, "unit": "MP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"OneDC decode, synthetic {side}x{side} image (bounded sample of the 768x768 workload), "
-                               "random-init weights, host CPU"},
+        "config": {"workload": f"OneDC decode of 1 synthetic {side}x{side} image per step"
+                               + ("" if side == 768 else " (bounded sample of the 768x768 workload)")
+                               + ", random-init weights seed 0, host CPU"},
         "cpu_baseline": {"value": v, "unit": "MP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -277,20 +297,18 @@ def run_ours(args):
 
 
 def cpu_baseline(args):
-    """The oracle port timed on this box's host cores on a bounded sample (one 256x256 decode ~ 0.8 TFLOP fp32)."""
-    import torch
-    from oracle.decode import OneDCOracle
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    side = args.ref_size
-    sds = _state_dicts()
-    orc = OneDCOracle(sds[1], sds[0], sds[2])
+    """The oracle port timed on this box's host cores on a bounded sample of the workload (~10-30 s of CPU work):
+    two decodes of the 768x768 workload itself when they fit, else of a smaller square image."""
+    orc, cores, side, t256 = _oracle_and_size(args, (2, 30.0))
     stream, _, _ = orc.codec.make_stream(side, side, seed=1234)
+    n = 2 if side > 256 else 8
     t0 = time.perf_counter()
-    orc.decode(stream)
-    dt = time.perf_counter() - t0
+    for _ in range(n):
+        orc.decode(stream)
+    dt = (time.perf_counter() - t0) / n
     return {"value": side * side * MP / dt, "unit": "MP/s", "cores": cores, "kind": "port",
-            "sample": f"one synthetic {side}x{side} stream, full decode path (MP/s is size-normalised), fp32 torch CPU, {dt:.1f} s"}
+            "sample": f"{n} x one synthetic {side}x{side} stream, full decode path incl. rANS (MP/s is size-normalised), "
+                      f"fp32 torch CPU, {dt * n:.1f} s"}
 
 
 def main():
@@ -301,7 +319,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=768)
     ap.add_argument("--batch", type=int, default=1)
-    ap.add_argument("--ref-size", type=int, default=256)
+    ap.add_argument("--ref-size", type=int, default=0, help="side of the CPU sample image; 0 = largest that fits the time budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch kernels from Python instead of replaying CUDA graphs")
     args = ap.parse_args()

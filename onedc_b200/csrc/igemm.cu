@@ -51,6 +51,11 @@ struct IgemmParams {
   // this kernel, not the tensor pipe.  A and B (weights) travel through separate rings.
   int colmode, cm_groups, cm_dx[3], cm_nt[3], cm_tap[3][3], cm_row[3][3], cm_miny, cm_rows;
   int a_slots, a_slot_bytes, b_slots, b_slot_bytes;
+  // transposed column-copy mode (cout <= 128): the weights are the M operand (128 output channels) and a 32 x 8 pixel
+  // box the N = 256 operand, D^T[cout][pixel].  With N = 128 every MMA reads 8 KB of operands per 64 clocks, which
+  // alone saturates the 128 B/clk of shared memory; N = 256 reads 12 KB per 128 clocks.  Accumulator lanes are then
+  // output channels and the epilogue stores one bf16 per lane (64 contiguous bytes per warp and pixel).
+  int transposed;
   // optional per-CTA role timing (onedc_igemm_set_debug): 16 clock counters per CTA, see tools/igemm_roles.py
   long long* dbg;
   // epilogue
@@ -354,6 +359,22 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long 
   *acc += clock64() - t0;
 }
 
+// Transposed tiles: every lane owns one output channel.  Adds its (sum, sum of squares) to the fp64 accumulators:
+// groups of cpg = cout / gn_groups consecutive channels (cpg a power of two <= 32) are folded by a butterfly first.
+__device__ __forceinline__ void flush_channel_stats(const IgemmParams& p, int img, int ch, bool ch_ok, float s1, float s2) {
+  const int cpg = p.cout / p.gn_groups;
+  if (!ch_ok) s1 = s2 = 0.f;
+  for (int o = 1; o < cpg; o <<= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (ch_ok && (ch & (cpg - 1)) == 0) {
+    double* dst = p.gn_acc + ((size_t)img * p.gn_groups + ch / cpg) * 2;
+    atomicAdd(dst, (double)s1);
+    atomicAdd(dst + 1, (double)s2);
+  }
+}
+
 // k-iteration index -> (tap, source, 64-channel chunk)
 struct KIter {
   int tap, src, kc;
@@ -533,13 +554,14 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     const uint32_t leader = elect_one();
     long long w_a = 0, w_b = 0, w_t = 0;
     const long long t_start = TIMED ? clock64() : 0;
-    const uint32_t idesc = umma_idesc_bf16(128, p.BN, 0, 0);
+    const uint32_t idesc = umma_idesc_bf16(128, p.transposed ? 256 : p.BN, 0, 0);
     // descriptor = constant high part | (shared address >> 4): advancing a slot / a row offset / 16 K elements is an add
     const uint64_t desc_hi = umma_smem_desc(0, 16, 1024);
     const uint32_t smem_enc = (smem0 & 0x3FFFF) >> 4;
     int it = 0;
     if (!SPLITK && p.colmode) {
       const int nch = p.kchunks[0] + p.kchunks[1], a_slots = p.a_slots, b_slots = p.b_slots, groups = p.cm_groups;
+      const bool transposed = p.transposed != 0;
       const uint32_t a_enc = (uint32_t)p.a_slot_bytes >> 4, b_enc = (uint32_t)p.b_slot_bytes >> 4;
       const uint32_t smem_b_enc = smem_enc + (uint32_t)a_slots * a_enc;
       int sa = 0, sb = 0;
@@ -560,8 +582,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
               mbar_wait_t<TIMED>(b_fb, pb, &w_b);
               tc_fence_after();
               if (leader) {
-                const uint64_t da = desc_hi | (uint64_t)(a_lo + row_enc);
-                const uint64_t db = desc_hi | (uint64_t)b_lo;
+                const uint64_t dpix = desc_hi | (uint64_t)(a_lo + row_enc);
+                const uint64_t dwgt = desc_hi | (uint64_t)b_lo;
+                const uint64_t da = transposed ? dwgt : dpix;        // M operand
+                const uint64_t db = transposed ? dpix : dwgt;        // N operand
                 umma_bf16(d_tmem, da, db, idesc, accumulate);
                 umma_bf16(d_tmem, da + 2, db + 2, idesc, 1);
                 umma_bf16(d_tmem, da + 4, db + 4, idesc, 1);
@@ -669,6 +693,82 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       const long long pix = ((long long)t.img * p.H + y) * p.W + x;
       const bool fast = p.vec_ok && (o0 + out_cols_tile <= p.ncols_out) && (out_cols_tile % 32 == 0) &&
                         (p.store_mode == ST_NORMAL || p.store_mode == ST_QUAD || (p.store_mode == ST_PIXSHUF && p.ps_c % 32 == 0));
+      if (!SPLITK && p.transposed) {
+        // ---- transposed tile: lane = output channel, TMEM column n = pixel (y0 + n / 8, x0 + n % 8)
+        const int ch = q * 32 + lane;
+        const bool ch_ok = ch < p.cout;
+        const float bias_v = bias_s[acc][ch];
+        if (p.gn_acc != nullptr && t.img != st_img) {
+          if (st_img >= 0) flush_channel_stats(p, st_img, ch, ch_ok, csum[0], csq[0]);
+          csum[0] = csq[0] = 0.f;
+          st_img = t.img;
+        }
+        float s1 = 0.f, s2 = 0.f;
+        const long long pix_img = (long long)t.img * p.H * p.W;
+        const int nx = p.W - t.x0 < 8 ? p.W - t.x0 : 8;                    // valid pixels per box row (warp-uniform)
+        // host guarantees: bf16 output, bf16 (or no) residual, activation none / LeakyReLU (max(v, slope v), slope 1 = none):
+        // the per-pixel body must stay tiny, it is unrolled 32 times
+        const float slope_eff = p.act == ACT_LRELU ? p.slope : 1.f;
+        const bool full_tile = ch_ok && t.y0 + 32 <= p.H && t.x0 + 8 <= p.W;
+        const __nv_bfloat16* resp = reinterpret_cast<const __nv_bfloat16*>(p.res);
+        __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out) + p.out_col_off + ch;
+        for (int c = member * 32; c < 256; c += 64) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c, r);
+          // 32 pixels = 4 box rows of 8: issue all the residual loads of the chunk before the TMEM data is needed
+          float rv[32];
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            const int yy = t.y0 + (c >> 3) + g;
+            const __nv_bfloat16* rrow = resp + (pix_img + (long long)yy * p.W + t.x0) * p.res_ld + ch;
+            const bool rok = resp != nullptr && ch_ok && yy < p.H;
+#pragma unroll
+            for (int jx = 0; jx < 8; jx++) rv[g * 8 + jx] = (rok && jx < nx) ? __bfloat162float(rrow[(long long)jx * p.res_ld]) : 0.f;
+          }
+          tmem_ld_wait();
+          if (full_tile) {
+            // interior tile: no per-pixel tests, pointers advance by constants (10 instructions per pixel)
+            __nv_bfloat16* op = outp + (pix_img + (long long)(t.y0 + (c >> 3)) * p.W + t.x0) * p.out_ld;
+            const long long row_skip = (long long)(p.W - 8) * p.out_ld;
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+#pragma unroll
+              for (int jx = 0; jx < 8; jx++) {
+                float v = __uint_as_float(r[g * 8 + jx]) + bias_v;
+                v = fmaxf(v, v * slope_eff) + rv[g * 8 + jx];
+                *op = __float2bfloat16(v);
+                op += p.out_ld;
+                s1 += v;
+                s2 += v * v;
+              }
+              op += row_skip;
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+              const int yy = t.y0 + (c >> 3) + g;
+              __nv_bfloat16* orow = outp + (pix_img + (long long)yy * p.W + t.x0) * p.out_ld;
+              const bool ook = ch_ok && yy < p.H;
+#pragma unroll
+              for (int jx = 0; jx < 8; jx++) {
+                if (ook && jx < nx) {
+                  float v = __uint_as_float(r[g * 8 + jx]) + bias_v;
+                  v = fmaxf(v, v * slope_eff) + rv[g * 8 + jx];
+                  orow[(long long)jx * p.out_ld] = __float2bfloat16(v);
+                  s1 += v;
+                  s2 += v * v;
+                }
+              }
+            }
+          }
+        }
+        csum[0] += s1;
+        csq[0] += s2;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        continue;
+      }
       if (SPLITK) {
         long long tp = TIMED ? clock64() : 0;
         auto phase_mark = [&](int slot) {
@@ -908,7 +1008,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
     if (TIMED && threadIdx.x == 64) p.dbg[(size_t)blockIdx.x * 16 + 8] = clock64() - t_epi0;
-    if (p.gn_acc != nullptr && st_img >= 0) {
+    if (!SPLITK && p.transposed) {
+      if (p.gn_acc != nullptr && st_img >= 0) flush_channel_stats(p, st_img, q * 32 + lane, q * 32 + lane < p.cout, csum[0], csq[0]);
+    } else if (p.gn_acc != nullptr && st_img >= 0) {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         const int cl = member * 32 + k * 64;
@@ -1268,6 +1370,26 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
           p.colmode = 1;
           p.TH = 16;
           p.TW = 8;
+          // transposed variant for narrow outputs: one 128-channel M tile, N = 32 x 8 pixels
+          static const bool transp_on = getenv("ONEDC_TRANSPOSED") == nullptr || getenv("ONEDC_TRANSPOSED")[0] != '0';
+          const int tiles32x8 = p.n_img * ((p.H + 31) / 32) * ((p.W + 7) / 8);
+          const int cpg_t = d->gn_acc != nullptr && d->gn_groups > 0 ? d->cout / d->gn_groups : 1;
+          if (transp_on && !pair && d->cout <= 128 && d->cout >= 64 && p.n_tiles == 1 && d->store_mode == ST_NORMAL &&
+              d->out_dtype == DT_BF16 && (d->res == nullptr || (colmode_all && d->res_dtype == DT_BF16)) &&   // residual: 2-byte
+              // loads per lane and pixel make the epilogue the bottleneck (measured slower than the regular tile)
+              (d->act == ACT_NONE || (d->act == ACT_LRELU && d->slope > 0.f && d->slope <= 1.f)) &&
+              (colmode_all || tiles32x8 > sm_count()) && (cpg_t & (cpg_t - 1)) == 0 && cpg_t <= 32 &&
+              (d->gn_acc == nullptr || d->cout % d->gn_groups == 0)) {
+            p.transposed = 1;
+            p.TH = 32;
+            p.BN = 128;                                   // weight rows per tile (TMA box; rows >= cout are zero-filled)
+            p.cm_rows = 32 + maxy - miny;
+            p.a_slot_bytes = p.cm_rows * 1024;
+            p.b_slot_bytes = 128 * 128;
+            p.a_slots = 3;
+            p.b_slots = (kSmemBudget - p.a_slots * p.a_slot_bytes) / p.b_slot_bytes;
+            if (p.b_slots > kMaxStages) p.b_slots = kMaxStages;
+          }
           p.tiles_y = (p.H + p.TH - 1) / p.TH;
           p.tiles_x = (p.W + p.TW - 1) / p.TW;
           p.m_tiles = p.n_img * p.tiles_y * p.tiles_x;
@@ -1283,9 +1405,11 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
     const bool fast_all = p.vec_ok && (d->cout % p.BN == 0) && (p.BN % 32 == 0) &&
                           (d->store_mode == ST_NORMAL || d->store_mode == ST_QUAD) && p.BN <= 256;
     const int cpg = d->gn_groups > 0 ? d->cout / d->gn_groups : 0;
-    if (fast_all && d->gn_groups > 0 && d->cout % d->gn_groups == 0 && (cpg == 1 || cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32)) {
+    const bool cpg_ok = p.transposed ? (cpg >= 1 && cpg <= 32 && (cpg & (cpg - 1)) == 0)
+                                     : (cpg == 1 || cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32);
+    if ((fast_all || p.transposed) && d->gn_groups > 0 && d->cout % d->gn_groups == 0 && cpg_ok) {
       p.gn_acc = reinterpret_cast<double*>(d->gn_acc);
-      p.gn_ng = 32 / cpg;
+      p.gn_ng = cpg <= 32 ? 32 / cpg : 1;
       p.gn_groups = d->gn_groups;
       d->gn_fused_out = 1;
     }

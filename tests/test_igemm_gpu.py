@@ -225,3 +225,34 @@ def test_column_copy_mode_3x3(cuda, n, h, w, cin, cin2, cout):
         o = out.float().view(n, h * w, ng, cout // ng)
         want = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1).double()
         assert torch.allclose(got, want, rtol=2e-3, atol=1e-2 * float(want.abs().max()) * 1e-2)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,two,f32", [(1, 384, 384, 128, 128, False, False), (2, 100, 210, 256, 128, False, False),
+                                                    (1, 256, 256, 64, 96, True, False), (1, 320, 200, 128, 64, False, True)])   # fp32 output: regular tile
+def test_transposed_column_copy_mode(cuda, n, h, w, cin, cout, two, f32):
+    """Narrow outputs (cout <= 128) on many tiles run the transposed tile: weights as the M operand, 32x8 pixels as
+    N = 256, one bf16 store per lane.  Bias, residual, ragged edges, two sources, fp32 output and the fused GroupNorm
+    statistics must match torch / the SIMT checker."""
+    from onedc_b200 import ops
+    x = _mk((n, h, w, cin), cuda, 1)
+    x2 = _mk((n, h, w, cin), cuda, 5) if two else None
+    ct = cin * (2 if two else 1)
+    wt = _mk((cout, ct, 3, 3), "cpu", 2, scale=(ct * 9) ** -0.5).float()
+    b = _mk((cout,), "cpu", 3).float()
+    res = _mk((n, h, w, cout), cuda, 4)
+    cw = ops.ConvW(wt, b, cuda)
+    ops.gn_arena_reset(cuda)
+    od = torch.float32 if f32 else torch.bfloat16
+    out = ops.igemm(x, cw, x2=x2, res=res, stats=True, out_dtype=od)
+    ref = _ref_conv(x, cw.w.float().reshape(3, 3, cout, -1).permute(2, 3, 0, 1)[:, :ct].contiguous(), b.to(cuda), 3, 1, x2) + res.float()
+    _close(out, ref)
+    _close(ops.igemm(x, cw, x2=x2, res=res, impl=1, out_dtype=od), ref)
+    assert torch.equal(out, ops.igemm(x, cw, x2=x2, res=res, out_dtype=od)), "not deterministic"
+    acc = getattr(out, "_gn_acc", None)
+    assert acc is not None
+    torch.cuda.synchronize()
+    ng = cout if out._gn_chan else 32
+    got = acc[: n * ng * 2].view(n, ng, 2)
+    o = out.float().view(n, h * w, ng, cout // ng)
+    want = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1).double()
+    assert torch.allclose(got, want, rtol=3e-3, atol=1e-4 * float(want.abs().max()))
