@@ -12,62 +12,72 @@ __device__ __constant__ int kXor[4] = {0, 3, 2, 1};
 
 // ------------------------------------------------------------------------------------------------
 // scales (NHWC bf16, 4*c4 channels) -> int16 CDF indices in stream order [n][c4][h*w].
-// Block = 128 consecutive pixels of one image.  Phase 1 (thread = pixel): four 16-byte loads of the active
-// c4-channel slice, table lookup, indices to shared memory.  Phase 2 (thread = plane quarter): 16-byte
-// stores of 8 consecutive pixels of one plane, so every global access of the kernel is a full 16-byte vector.
+// Block = 128 consecutive pixels of one image, in four rounds of 32 pixels.  Phase 1: FOUR lanes share a pixel, each
+// takes one 16-byte vector (8 channels) of the pixel's active c4-channel slice, so a warp-wide load touches 8 pixels x
+// 64 contiguous bytes (thread-per-pixel touched 32 separate lines per load and was bound by the LSU, 47 % of HBM);
+// table lookup; indices to shared memory.  Phase 2 (thread = plane quarter): 16-byte stores of 8 consecutive pixels
+// of one plane.  The tile is swizzled (8-pixel group index XOR vector index) so that both phases are conflict-free.
 // The lookup uses the compact table: only bf16 patterns in [lo, hi) have an index other than 0 / 255
 // (lo = first pattern with index > 0, hi = first pattern with index 255), ~1.2 KB instead of 64 KB.
 template <int C4>
 __global__ void __launch_bounds__(128) scale_to_index_kernel(const __nv_bfloat16* scales, long long ld, const uint8_t* lut,
                                                              int lo, int hi, int16_t* idx_out, int step, int h, int w) {
+  static_assert(C4 == 32, "lane mapping assumes four 16-byte vectors per pixel");
   pdl_wait();
   __shared__ __align__(16) int16_t tile[C4][128 + 8];
   __shared__ uint8_t tab[2048];
   const long long hw = (long long)h * w;
   const int n = blockIdx.y;
   const long long p0 = (long long)blockIdx.x * 128;
-  const long long p = p0 + threadIdx.x;
   const int span = hi - lo;
+  const int v = threadIdx.x & 3, pq = threadIdx.x >> 2;
+  // the four loads of this thread first (independent of the table)
+  uint4 q[4];
+  bool okp[4];
+#pragma unroll
+  for (int it = 0; it < 4; it++) {
+    const long long p = p0 + it * 32 + pq;
+    okp[it] = p < hw;
+    q[it] = make_uint4(0, 0, 0, 0);
+    if (okp[it]) {
+      const int y = (int)p / w, x = (int)p - y * w;      // h * w < 2^31 (checked by the host wrapper)
+      const int g = (2 * (y & 1) + (x & 1)) ^ kXor[step];
+      q[it] = __ldg(reinterpret_cast<const uint4*>(scales + ((long long)n * hw + p) * ld + g * C4) + v);
+    }
+  }
   for (int i = threadIdx.x; i < span; i += 128) tab[i] = __ldg(lut + lo + i);
   __syncthreads();
-  if (p < hw) {
-    const int y = (int)(p / w), x = (int)(p - (long long)y * w);
-    const int g = (2 * (y & 1) + (x & 1)) ^ kXor[step];
-    const uint4* src = reinterpret_cast<const uint4*>(scales + ((long long)n * hw + p) * ld + g * C4);
-    uint4 q[C4 / 8];
 #pragma unroll
-    for (int v = 0; v < C4 / 8; v++) q[v] = __ldg(src + v);
+  for (int it = 0; it < 4; it++) {
+    const int pl = (it * 32 + pq) ^ (v << 3);                      // swizzled pixel slot
+    const uint32_t wds[4] = {q[it].x, q[it].y, q[it].z, q[it].w};
 #pragma unroll
-    for (int v = 0; v < C4 / 8; v++) {
-      const uint32_t wds[4] = {q[v].x, q[v].y, q[v].z, q[v].w};
+    for (int j = 0; j < 4; j++) {
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-#pragma unroll
-        for (int hlf = 0; hlf < 2; hlf++) {
-          const int bits = hlf ? (int)(wds[j] >> 16) : (int)(wds[j] & 0xFFFFu);   // sign bit set => >= 0x8000 => 0
-          int r = 0;
-          if (bits >= hi && bits <= 0x7F80) r = 255;          // NaN patterns (> 0x7F80) keep index 0 like the table
-          else if (bits >= lo && bits < hi) r = tab[bits - lo];
-          tile[v * 8 + 2 * j + hlf][threadIdx.x] = (int16_t)r;
-        }
+      for (int hlf = 0; hlf < 2; hlf++) {
+        const int bits = hlf ? (int)(wds[j] >> 16) : (int)(wds[j] & 0xFFFFu);   // sign bit set => >= 0x8000 => 0
+        int r = 0;
+        if (bits >= hi && bits <= 0x7F80) r = 255;          // NaN patterns (> 0x7F80) keep index 0 like the table
+        else if (bits >= lo && bits < hi) r = tab[bits - lo];
+        tile[v * 8 + 2 * j + hlf][pl] = (int16_t)r;
       }
     }
   }
   __syncthreads();
   if ((hw & 7) == 0 && p0 + 128 <= hw) {
     // thread = (plane c, 32-pixel quarter): 4 x 16-byte stores
+    const int c = threadIdx.x >> 2, qx = (threadIdx.x & 3) * 32, sw = (c >> 3) & 3;
+    const uint4* s4 = reinterpret_cast<const uint4*>(&tile[c][qx]);
+    uint4* d4 = reinterpret_cast<uint4*>(idx_out + ((long long)n * C4 + c) * hw + p0 + qx);
 #pragma unroll
-    for (int r = 0; r < C4 / 32; r++) {
-      const int c = r * 32 + (threadIdx.x >> 2), qx = (threadIdx.x & 3) * 32;
-      const uint4* s4 = reinterpret_cast<const uint4*>(&tile[c][qx]);
-      uint4* d4 = reinterpret_cast<uint4*>(idx_out + ((long long)n * C4 + c) * hw + p0 + qx);
-#pragma unroll
-      for (int i = 0; i < 4; i++) d4[i] = s4[i];
-    }
-  } else if (p < hw) {
-    int16_t* dst = idx_out + (long long)n * C4 * hw + p;
+    for (int i = 0; i < 4; i++) d4[i] = s4[i ^ sw];
+  } else {
+    const long long p = p0 + threadIdx.x;
+    if (p < hw) {
+      int16_t* dst = idx_out + (long long)n * C4 * hw + p;
 #pragma unroll 8
-    for (int c = 0; c < C4; c++) dst[(long long)c * hw] = tile[c][threadIdx.x];
+      for (int c = 0; c < C4; c++) dst[(long long)c * hw] = tile[c][threadIdx.x ^ (((c >> 3) & 3) << 3)];
+    }
   }
 }
 
@@ -93,62 +103,75 @@ __global__ void build_indexes_kernel(const void* scales, int dtype, const uint8_
 // ------------------------------------------------------------------------------------------------
 // y_hat[n,y,x,g*C4+c] = bf16( sym[n][c][y*w+x] + means[n,y,x,g*C4+c] )   (sym may be null: means only)
 // MODE 0: decode (sym given or null).  MODE 1: encode twin, sym is OUTPUT = clamp(rint(y - means)).
+// Same thread mapping as scale_to_index_kernel: plane-major 16-byte accesses on the symbol side, four lanes per
+// pixel (one 16-byte vector each) on the NHWC side, swizzled shared-memory tile in between.
 template <int C4, int MODE>
 __global__ void __launch_bounds__(128) dequant_kernel(int16_t* sym, const __nv_bfloat16* yin, long long yin_ld,
                                                       const __nv_bfloat16* means, long long means_ld, __nv_bfloat16* y_hat,
                                                       long long y_ld, int step, int h, int w) {
+  static_assert(C4 == 32, "lane mapping assumes four 16-byte vectors per pixel");
   pdl_wait();
   __shared__ __align__(16) int16_t tile[C4][128 + 8];
   const long long hw = (long long)h * w;
   const int n = blockIdx.y;
-  const long long p = (long long)blockIdx.x * 128 + threadIdx.x;
-  const bool ok = p < hw;
   const long long p0 = (long long)blockIdx.x * 128;
   const bool vec = ((hw & 7) == 0) && (p0 + 128 <= hw);
+  const int v = threadIdx.x & 3, pq = threadIdx.x >> 2;
+  // NHWC side first: the loads do not depend on the symbols
+  uint4 mq[4], yq[4];
+  bool okp[4];
+  int gq[4];
+#pragma unroll
+  for (int it = 0; it < 4; it++) {
+    const long long p = p0 + it * 32 + pq;
+    okp[it] = p < hw;
+    mq[it] = yq[it] = make_uint4(0, 0, 0, 0);
+    gq[it] = 0;
+    if (okp[it]) {
+      const int y = (int)p / w, x = (int)p - y * w;      // h * w < 2^31 (checked by the host wrapper)
+      gq[it] = (2 * (y & 1) + (x & 1)) ^ kXor[step];
+      const long long pix = (long long)n * hw + p;
+      mq[it] = __ldg(reinterpret_cast<const uint4*>(means + pix * means_ld + gq[it] * C4) + v);
+      if (MODE == 1) yq[it] = __ldg(reinterpret_cast<const uint4*>(yin + pix * yin_ld + gq[it] * C4) + v);
+    }
+  }
   if (MODE == 0 && sym != nullptr) {
     if (vec) {
+      // thread = (plane c, 32-pixel quarter): 4 x 16-byte loads
+      const int c = threadIdx.x >> 2, qx = (threadIdx.x & 3) * 32, sw = (c >> 3) & 3;
+      const uint4* s4 = reinterpret_cast<const uint4*>(sym + ((long long)n * C4 + c) * hw + p0 + qx);
+      uint4* d4 = reinterpret_cast<uint4*>(&tile[c][qx]);
 #pragma unroll
-      for (int r = 0; r < C4 / 32; r++) {       // thread = (plane c, 32-pixel quarter): 4 x 16-byte loads
-        const int c = r * 32 + (threadIdx.x >> 2), qx = (threadIdx.x & 3) * 32;
-        const uint4* s4 = reinterpret_cast<const uint4*>(sym + ((long long)n * C4 + c) * hw + p0 + qx);
-        uint4* d4 = reinterpret_cast<uint4*>(&tile[c][qx]);
-#pragma unroll
-        for (int i = 0; i < 4; i++) d4[i] = __ldg(s4 + i);
-      }
-    } else if (ok) {
-      const int16_t* src = sym + (long long)n * C4 * hw + p;
+      for (int i = 0; i < 4; i++) d4[i ^ sw] = __ldg(s4 + i);
+    } else {
+      const long long p = p0 + threadIdx.x;
+      if (p < hw) {
+        const int16_t* src = sym + (long long)n * C4 * hw + p;
 #pragma unroll 8
-      for (int c = 0; c < C4; c++) tile[c][threadIdx.x] = src[(long long)c * hw];
+        for (int c = 0; c < C4; c++) tile[c][threadIdx.x ^ (((c >> 3) & 3) << 3)] = src[(long long)c * hw];
+      }
     }
     __syncthreads();
   }
-  if (ok) {
-    const int y = (int)(p / w), x = (int)(p - (long long)y * w);
-    const int g = (2 * (y & 1) + (x & 1)) ^ kXor[step];
-    const long long pix = (long long)n * hw + p;
-    const uint4* mp = reinterpret_cast<const uint4*>(means + pix * means_ld + g * C4);
-    uint4* dst = reinterpret_cast<uint4*>(y_hat + pix * y_ld + g * C4);
-    const uint4* yp = MODE == 1 ? reinterpret_cast<const uint4*>(yin + pix * yin_ld + g * C4) : nullptr;
 #pragma unroll
-    for (int v = 0; v < C4 / 8; v++) {
-      uint4 m = __ldg(mp + v);
-      uint32_t mw[4] = {m.x, m.y, m.z, m.w}, ow[4];
-      uint32_t yw[4] = {0, 0, 0, 0};
-      if (MODE == 1) {
-        uint4 yy = __ldg(yp + v);
-        yw[0] = yy.x; yw[1] = yy.y; yw[2] = yy.z; yw[3] = yy.w;
-      }
+  for (int it = 0; it < 4; it++) {
+    const int pl = (it * 32 + pq) ^ (v << 3);
+    if (okp[it]) {
+      const long long pix = (long long)n * hw + p0 + it * 32 + pq;
+      const uint32_t mw[4] = {mq[it].x, mq[it].y, mq[it].z, mq[it].w};
+      const uint32_t yw[4] = {yq[it].x, yq[it].y, yq[it].z, yq[it].w};
+      uint32_t ow[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         float q0, q1;
         if (MODE == 1) {
           q0 = fminf(fmaxf(rintf(bf16lo(yw[j]) - bf16lo(mw[j])), -30000.f), 30000.f);
           q1 = fminf(fmaxf(rintf(bf16hi(yw[j]) - bf16hi(mw[j])), -30000.f), 30000.f);
-          tile[v * 8 + 2 * j][threadIdx.x] = (int16_t)q0;
-          tile[v * 8 + 2 * j + 1][threadIdx.x] = (int16_t)q1;
+          tile[v * 8 + 2 * j][pl] = (int16_t)q0;
+          tile[v * 8 + 2 * j + 1][pl] = (int16_t)q1;
         } else if (sym != nullptr) {
-          q0 = (float)tile[v * 8 + 2 * j][threadIdx.x];
-          q1 = (float)tile[v * 8 + 2 * j + 1][threadIdx.x];
+          q0 = (float)tile[v * 8 + 2 * j][pl];
+          q1 = (float)tile[v * 8 + 2 * j + 1][pl];
         } else {
           q0 = q1 = 0.f;
         }
@@ -158,32 +181,29 @@ __global__ void __launch_bounds__(128) dequant_kernel(int16_t* sym, const __nv_b
         q1 = __bfloat162float(__float2bfloat16(q1));
         ow[j] = pack_bf16x2(q0 + bf16lo(mw[j]), q1 + bf16hi(mw[j]));
       }
-      dst[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-    }
-    if (step == 0) {   // y_hat_so_far starts as (..)*mask_0: zero everywhere else
-      for (int og = 0; og < 4; og++) {
-        if (og == g) continue;
-        uint4* z = reinterpret_cast<uint4*>(y_hat + pix * y_ld + og * C4);
+      reinterpret_cast<uint4*>(y_hat + pix * y_ld + gq[it] * C4)[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      if (step == 0) {   // y_hat_so_far starts as (..)*mask_0: zero everywhere else
 #pragma unroll
-        for (int v = 0; v < C4 / 8; v++) z[v] = make_uint4(0, 0, 0, 0);
+        for (int og = 0; og < 4; og++)
+          if (og != gq[it]) reinterpret_cast<uint4*>(y_hat + pix * y_ld + og * C4)[v] = make_uint4(0, 0, 0, 0);
       }
     }
   }
   if (MODE == 1) {
     __syncthreads();
     if (vec) {
+      const int c = threadIdx.x >> 2, qx = (threadIdx.x & 3) * 32, sw = (c >> 3) & 3;
+      const uint4* s4 = reinterpret_cast<const uint4*>(&tile[c][qx]);
+      uint4* d4 = reinterpret_cast<uint4*>(sym + ((long long)n * C4 + c) * hw + p0 + qx);
 #pragma unroll
-      for (int r = 0; r < C4 / 32; r++) {
-        const int c = r * 32 + (threadIdx.x >> 2), qx = (threadIdx.x & 3) * 32;
-        const uint4* s4 = reinterpret_cast<const uint4*>(&tile[c][qx]);
-        uint4* d4 = reinterpret_cast<uint4*>(sym + ((long long)n * C4 + c) * hw + p0 + qx);
-#pragma unroll
-        for (int i = 0; i < 4; i++) d4[i] = s4[i];
-      }
-    } else if (ok) {
-      int16_t* o = sym + (long long)n * C4 * hw + p;
+      for (int i = 0; i < 4; i++) d4[i] = s4[i ^ sw];
+    } else {
+      const long long p = p0 + threadIdx.x;
+      if (p < hw) {
+        int16_t* o = sym + (long long)n * C4 * hw + p;
 #pragma unroll 8
-      for (int c = 0; c < C4; c++) o[(long long)c * hw] = tile[c][threadIdx.x];
+        for (int c = 0; c < C4; c++) o[(long long)c * hw] = tile[c][threadIdx.x ^ (((c >> 3) & 3) << 3)];
+      }
     }
   }
 }
@@ -359,7 +379,7 @@ extern "C" int onedc_scale_to_index(const void* scales, int64_t ld, const uint8_
   ONEDC_CHECK(c4 == 32 && step >= 0 && step < 4 && ld % 8 == 0, "scale_to_index: c4 must be 32, step in 0..3");
   ONEDC_CHECK(lut_lo >= 0 && lut_hi >= lut_lo && lut_hi - lut_lo <= 2048 && lut_hi <= 0x8000,
               "scale_to_index: compact table range [lo, hi) must span at most 2048 positive bf16 patterns");
-  ONEDC_CHECK(n_img <= 65535, "scale_to_index: batch too large");
+  ONEDC_CHECK(n_img <= 65535 && (long long)h * w < (1ll << 31), "scale_to_index: batch or plane too large");
   const long long hw = (long long)h * w;
   dim3 grid((unsigned)((hw + 127) / 128), n_img);
   ONEDC_CUDA(launch_k(scale_to_index_kernel<32>, grid, 128, 0, (cudaStream_t)stream, (const __nv_bfloat16*)scales, ld, lut, lut_lo, lut_hi, idx_out,
@@ -378,7 +398,8 @@ extern "C" int onedc_build_indexes(const void* scales, int32_t in_dtype, const u
 
 extern "C" int onedc_dequant_accum(const int16_t* sym, const void* means, int64_t means_ld, void* y_hat, int64_t y_ld,
                                    int32_t step, int32_t n_img, int32_t h, int32_t w, int32_t c4, void* stream) {
-  ONEDC_CHECK(c4 == 32 && step >= 0 && step < 4 && means_ld % 8 == 0 && y_ld % 8 == 0, "dequant_accum: bad arguments");
+  ONEDC_CHECK(c4 == 32 && step >= 0 && step < 4 && means_ld % 8 == 0 && y_ld % 8 == 0 && (long long)h * w < (1ll << 31),
+              "dequant_accum: bad arguments");
   const long long hw = (long long)h * w;
   dim3 grid((unsigned)((hw + 127) / 128), n_img);
   ONEDC_CUDA(launch_k(dequant_kernel<32, 0>, grid, 128, 0, (cudaStream_t)stream, const_cast<int16_t*>(sym), nullptr, 0,
@@ -391,7 +412,8 @@ extern "C" int onedc_dequant_accum(const int16_t* sym, const void* means, int64_
 extern "C" int onedc_quantize_residual(const void* y, int64_t y_in_ld, const void* means, int64_t means_ld, int16_t* sym,
                                        void* y_hat, int64_t y_ld, int32_t step, int32_t n_img, int32_t h, int32_t w,
                                        int32_t c4, void* stream) {
-  ONEDC_CHECK(c4 == 32 && step >= 0 && step < 4 && means_ld % 8 == 0 && y_ld % 8 == 0 && y_in_ld % 8 == 0,
+  ONEDC_CHECK(c4 == 32 && step >= 0 && step < 4 && means_ld % 8 == 0 && y_ld % 8 == 0 && y_in_ld % 8 == 0 &&
+                  (long long)h * w < (1ll << 31),
               "quantize_residual: bad arguments");
   const long long hw = (long long)h * w;
   dim3 grid((unsigned)((hw + 127) / 128), n_img);
