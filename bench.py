@@ -208,6 +208,23 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_e2e = parallel.reduce_max((time.perf_counter() - t0) / args.steps)
     parallel.barrier()
+    # ---- throughput API: `depth` images in flight per GPU (host rANS of one image under the kernels of another)
+    pipe = None
+    if use_graphs and args.pipeline > 1 and B == 1:
+        extra = [model.codec_model.compress_synthetic(H, W, seed=4321 + rank * 1000 + i)[0] for i in range(3)]
+        many = [(streams + extra)[i % 4] for i in range(max(args.steps, 4 * args.pipeline))]
+        pd = model.pipelined(H, W, args.pipeline)
+        pd.decode_many(many[: 2 * args.pipeline])                       # warm-up
+        parallel.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pd.decode_many(many)
+        torch.cuda.synchronize()
+        t_pipe = parallel.reduce_max(time.perf_counter() - t0)
+        parallel.barrier()
+        pipe = {"value": len(many) * world * H * W * MP / t_pipe, "unit": "MP/s", "images_per_gpu": len(many),
+                "images_in_flight": args.pipeline, "ms_per_image": t_pipe * 1e3 / len(many),
+                "api": "model.decode_many(streams): host bytes -> host images, host rANS and all copies inside"}
     clocks = sampler.stop() if rank == 0 else None
     # ---- roofline of the dominant kernel (tcgen05 implicit GEMM, ~420 launches per step).  Its time inside the
     #      timed region is measured live as a DIFFERENCE of CUDA-event timings: the same graph-replayed step with and
@@ -291,6 +308,8 @@ def run_ours(args):
         "host_rans_ms_per_step": getattr(gd, "last_rans_ms", None) if use_graphs else None,
         "gpu_launches": launches, "roofline": roof, "clocks": clocks,
     }
+    if pipe is not None:
+        res["e2e_pipelined"] = pipe
     if not args.no_cpu_baseline and world >= 1:
         res["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(res))
@@ -321,6 +340,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--ref-size", type=int, default=0, help="side of the CPU sample image; 0 = largest that fits the time budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=3, help="images in flight for the extra e2e_pipelined figure (0/1 = skip)")
     ap.add_argument("--eager", action="store_true", help="launch kernels from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -22,10 +22,13 @@ from .entropy_models import StreamDecoder
 
 
 class GraphedDecoder:
-    def __init__(self, model, batch, height, width):
+    def __init__(self, model, batch, height, width, lane_base=0):
+        """lane_base: first of the two scratch lanes (split-K workspace, GroupNorm accumulators) this decoder's graphs
+        are captured against; decoders that replay CONCURRENTLY (PipelinedDecoder) must not share lanes."""
         assert height % 64 == 0 and width % 64 == 0, "graphs are keyed by the padded size"
         self.model, self.codec = model, model.codec_model
         self.B, self.H, self.W = batch, height, width
+        self.lane_base = lane_base
         dev = model.device
         self.dev = dev
         self.hz, self.wz = height // 64, width // 64
@@ -69,7 +72,7 @@ class GraphedDecoder:
         """Semantic branch (needs only z): semantic adaptor + the sem_up half of g_s.  Replayed on a side stream so
         it fills the GPU while the host runs rANS; uses its own scratch lane."""
         c = self.codec
-        ops.SCRATCH_LANE = 1
+        ops.SCRATCH_LANE = self.lane_base + 1
         try:
             codes = ops.fsq_codes(self.z_dev)
             z_sem = ops.igemm(codes, c.hyper.feat_in, act=ops.ACT_LRELU, slope=0.01)
@@ -77,7 +80,7 @@ class GraphedDecoder:
             self.cat = c.dec.alloc_cat(self.B, self.h16, self.w16, self.dev)
             c.dec.sem_path(self.y_sem, self.cat)
         finally:
-            ops.SCRATCH_LANE = 0
+            ops.SCRATCH_LANE = self.lane_base
 
     def _seg4(self):
         c = self.codec
@@ -95,6 +98,13 @@ class GraphedDecoder:
         """Warm up eagerly once (function attributes, allocator), then capture the five segments into one pool."""
         if self.graphs is not None:
             return
+        ops.SCRATCH_LANE = self.lane_base
+        try:
+            self._capture()
+        finally:
+            ops.SCRATCH_LANE = 0
+
+    def _capture(self):
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s), torch.no_grad():
@@ -120,6 +130,7 @@ class GraphedDecoder:
         if self.g_res is not None:
             return
         from . import lib
+        assert self.lane_base == 0, "the resident leg is only captured on the default lanes"
         with torch.no_grad():
             self.model.decode_resident(self.z_dev, self.syms_res)
             torch.cuda.synchronize()
@@ -176,3 +187,62 @@ class GraphedDecoder:
         self.capture_resident()
         self.g_res.replay()
         return self.img_res
+
+
+class PipelinedDecoder:
+    """Several images in flight on one GPU.  One image is a serial chain -- four
+    (graph replay -> D2H indices -> host rANS -> H2D symbols) rounds and the final graph -- during which the GPU idles
+    while the host decodes and the host idles while the GPU runs, and ~250 of its launches are too small to fill the
+    GPU.  `depth` GraphedDecoder slots, each with its own CUDA stream, pinned buffers, graphs and scratch lanes, are
+    driven by `depth` host threads that pull streams from a queue: the rANS call releases the GIL, so one slot's
+    entropy decode overlaps another slot's kernels, and small kernels of different images share the GPU.  Results are
+    bit-identical to decoding the images one by one (same graphs, same kernels)."""
+
+    def __init__(self, model, height, width, depth=2):
+        self.model, self.H, self.W, self.depth = model, height, width, depth
+        self.slots = [GraphedDecoder(model, 1, height, width, lane_base=2 * (i + 1)) for i in range(depth)]
+        self.streams = [torch.cuda.Stream(device=model.device) for _ in range(depth)]
+        for sl, st in zip(self.slots, self.streams):          # capture up front, one after the other
+            with torch.cuda.stream(st):
+                sl.capture()
+        torch.cuda.synchronize()
+
+    def decode_many(self, streams, out=None):
+        """streams: reference-format containers of this padded size -> list of fp32 [1,3,H,W] host tensors (cropped),
+        in input order.  `out`: optional preallocated pinned tensor [len(streams),3,H,W] to receive the padded images."""
+        import queue
+        import threading
+        n = len(streams)
+        q = queue.SimpleQueue()
+        for i in range(n):
+            q.put(i)
+        results = [None] * n
+        errors = []
+
+        def worker(k):
+            slot, st = self.slots[k], self.streams[k]
+            try:
+                with torch.cuda.stream(st), torch.no_grad():
+                    while True:
+                        try:
+                            i = q.get_nowait()
+                        except queue.Empty:
+                            return
+                        host, hdrs = slot.decode([streams[i]])
+                        d = hdrs[0]
+                        if out is not None:
+                            out[i].copy_(host[0])
+                            results[i] = out[i:i + 1, :, :d["height"], :d["width"]]
+                        else:
+                            results[i] = host[:, :, :d["height"], :d["width"]].clone()
+            except Exception as e:                             # surfaced to the caller below
+                errors.append(e)
+
+        threads = [threading.Thread(target=worker, args=(k,)) for k in range(self.depth)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return results

@@ -100,6 +100,21 @@ class SD15_1step_codec_stage1:
         img = self.generate(x_hat, y_sem)
         return [img[i:i + 1, :, :d["height"], :d["width"]] for i, d in enumerate(hdrs)]
 
+    def pipelined(self, pad_h, pad_w, depth=2):
+        """Decoder that keeps `depth` images of this padded size in flight on the GPU (graphs.PipelinedDecoder)."""
+        from .graphs import PipelinedDecoder
+        key = ("pipe", pad_h, pad_w, depth)
+        if key not in self._graphed:
+            self._graphed[key] = PipelinedDecoder(self, pad_h, pad_w, depth)
+        return self._graphed[key]
+
+    @torch.no_grad()
+    def decode_many(self, streams, depth=2):
+        """Throughput API: same-size streams -> list of fp32 [1,3,H,W] HOST tensors, several images in flight."""
+        from . import bitstream
+        d0 = bitstream.decode_i(streams[0], 14, 64)
+        return self.pipelined(d0["pad_height"], d0["pad_width"], depth).decode_many(streams)
+
     @torch.no_grad()
     def decode_resident(self, z_idx, syms):
         """Device-resident decode (bench `value` leg): inputs already in HBM, padded image left in HBM."""

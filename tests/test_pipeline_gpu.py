@@ -201,3 +201,16 @@ def test_programmatic_dependent_launch_is_bit_identical(bundle):
         lib.set_pdl(old)
     for o in outs[1:]:
         assert torch.equal(o, outs[0]), "PDL changed the decoded image"
+
+
+def test_pipelined_decode_matches_one_by_one(bundle):
+    """model.decode_many keeps two images in flight (two graph sets on two streams and scratch lanes, host rANS of one
+    image under the kernels of the other): every image must equal the one-at-a-time graph decode bit for bit."""
+    model = bundle["model"]
+    streams = [bundle["stream"]] + [model.codec_model.compress_synthetic(H, W, seed=2000 + i)[0] for i in range(4)]
+    singles = [model.decode(stream=s).cpu() for s in streams]
+    for depth in (2, 3):
+        many = model.decode_many(streams, depth=depth)
+        assert len(many) == len(streams)
+        for a, b in zip(singles, many):
+            assert torch.equal(a, b), "pipelined decode differs from the single-image decode"
