@@ -43,7 +43,9 @@ PROTOTYPES = {
     "onedc_set_pdl": (C.c_int, [C.c_int]),
     "onedc_igemm": (C.c_int, [C.POINTER(IgemmDesc), _vp]),
     "onedc_igemm_set_debug": (None, [_vp]),
-    "onedc_attention": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
+    "onedc_attention_set_plan": (None, [_i32, _i32]),
+    "onedc_attention_ws_floats": (_i64, [_i32, _i32, _i32, _i32, _i32]),
+    "onedc_attention": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _i64, _vp]),
     "onedc_groupnorm_ws_floats": (_i64, [_i32, _i64, _i32]),
     "onedc_groupnorm_stats": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "onedc_groupnorm_apply": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _i32, _f32,

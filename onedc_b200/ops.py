@@ -258,6 +258,19 @@ def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None
     return out
 
 
+_attn_scratch = {}
+
+
+def _attn_ws(device, floats):
+    """fp32 scratch for key-range-split attention launches, per (device, scratch lane), grown on demand (the eager
+    warm-up pass that precedes every graph capture sizes it, so captures never allocate it from a graph pool)."""
+    key = (str(device), SCRATCH_LANE)
+    buf = _attn_scratch.get(key)
+    if buf is None or buf.numel() < floats:
+        buf = _attn_scratch[key] = torch.empty(int(floats), device=device, dtype=torch.float32)
+    return buf
+
+
 def attention(q, k, v, out, heads, head_dim, scale=None, impl=None):
     """q [B,Sq,*], k/v [B,Skv,*] channel-slice views (head h at columns h*d), out [B,Sq,heads*d] view."""
     lib = L.load()
@@ -270,9 +283,12 @@ def attention(q, k, v, out, heads, head_dim, scale=None, impl=None):
     scale = head_dim ** -0.5 if scale is None else scale
     if "attention" in SKIP:
         return out
+    need = int(lib.onedc_attention_ws_floats(b, heads, head_dim, sq, skv))
+    ws = _attn_ws(q.device, need) if need > 0 else None
     e0 = _prof_begin()
     L.check(lib.onedc_attention(q.data_ptr(), q.stride(1), k.data_ptr(), v.data_ptr(), k.stride(1), out.data_ptr(),
                                 out.stride(1), b, heads, head_dim, sq, skv, scale, IMPL if impl is None else impl,
+                                0 if ws is None else ws.data_ptr(), 0 if ws is None else ws.numel(),
                                 _stream()), "onedc_attention")
     _prof_end("attention", e0, 4.0 * b * heads * sq * skv * head_dim)
     return out

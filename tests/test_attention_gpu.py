@@ -75,3 +75,30 @@ def test_unfused_matches_sdpa(cuda, b, heads, d, s):
     ref = _ref(q, k, v, heads, d, scale=scale)
     err = (out.float() - ref).abs().max().item()
     assert err < 2e-2, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("plan", [(1, 1), (2, 3), (1, 3), (2, 4)])
+@pytest.mark.parametrize("b,heads,d,sq,skv", [(1, 8, 40, 2304, 5000), (2, 8, 40, 1152, 1152), (1, 8, 64, 2304, 1100), (1, 8, 80, 576, 2304)])
+def test_flash_launch_plans(cuda, b, heads, d, sq, skv, plan):
+    """The non-default launch plans: one S buffer / three CTAs per SM, and the key range split over several CTAs per
+    query tile (fp32 partial O + running max / sum, merged by attention_merge_kernel): ragged last block, batch > 1,
+    d = 64 and a head_dim that cannot take the one-buffer variant."""
+    from onedc_b200 import lib, ops
+    L = lib.load()
+    L.onedc_attention_set_plan(*plan)
+    try:
+        if plan[1] > 1:
+            assert L.onedc_attention_ws_floats(b, heads, d, sq, skv) > 0
+        c = heads * d
+        q = _mk((b, sq, c), cuda, 1)
+        kv = _mk((b, skv, 2 * c), cuda, 2)
+        out = torch.zeros((b, sq, c), device=cuda, dtype=torch.bfloat16)
+        ops.attention(q, kv[:, :, :c], kv[:, :, c:], out, heads, d)
+        ref = _ref(q, kv[:, :, :c], kv[:, :, c:], heads, d)
+        err = (out.float() - ref).abs().max().item()
+        assert err < 2e-2, f"max abs err {err}"
+        out2 = torch.zeros_like(out)
+        ops.attention(q, kv[:, :, :c], kv[:, :, c:], out2, heads, d)
+        assert torch.equal(out, out2)
+    finally:
+        L.onedc_attention_set_plan(0, 0)
