@@ -121,6 +121,11 @@ typedef struct {
   void* gn_acc;
   int32_t gn_groups;
   int32_t gn_fused_out;
+  /* optional L2 prefetch hint: a device range (16-byte aligned, size a multiple of 16) that a later launch will read
+   * -- in practice the NEXT layer's weights, which would otherwise arrive from DRAM at the head of that launch; the
+   * CTAs issue cp.async.bulk.prefetch.L2 for disjoint slices of it before starting their own work */
+  const void* prefetch_ptr;
+  int64_t prefetch_bytes;
 } onedc_igemm_desc;
 
 /* diagnostics: when set (device pointer to 148 x 16 int64, zeroed by the caller) every igemm CTA records clock

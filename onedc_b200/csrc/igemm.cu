@@ -56,6 +56,8 @@ struct IgemmParams {
   // alone saturates the 128 B/clk of shared memory; N = 256 reads 12 KB per 128 clocks.  Accumulator lanes are then
   // output channels and the epilogue stores one bf16 per lane (64 contiguous bytes per warp and pixel).
   int transposed;
+  const uint8_t* pf_ptr;  // optional L2 prefetch hint (the next layer's weights)
+  long long pf_bytes;
   // optional per-CTA role timing (onedc_igemm_set_debug): 16 clock counters per CTA, see tools/igemm_roles.py
   long long* dbg;
   // epilogue
@@ -408,21 +410,18 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   const int lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kMaxStages; s++) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int s = 0; s < 4; s++) {
-      mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], 1);
-    }
-    for (int a = 0; a < 2; a++) {
-      mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], kEpiWarps);   // one arrive per epilogue warp
-    }
-    fence_mbar_init();
+  // barrier init spread over the lanes of warp 0 (28 serial mbarrier.init cost ~0.3 us at the head of every launch)
+  if (threadIdx.x < kMaxStages) {
+    mbar_init(&full_bar[threadIdx.x], 1);
+    mbar_init(&empty_bar[threadIdx.x], 1);
+  } else if (threadIdx.x < kMaxStages + 4) {
+    mbar_init(&a_full[threadIdx.x - kMaxStages], 1);
+    mbar_init(&a_empty[threadIdx.x - kMaxStages], 1);
+  } else if (threadIdx.x < kMaxStages + 6) {
+    mbar_init(&tmem_full[threadIdx.x - kMaxStages - 4], 1);
+    mbar_init(&tmem_empty[threadIdx.x - kMaxStages - 4], kEpiWarps);   // one arrive per epilogue warp
   }
+  if (threadIdx.x < kMaxStages + 6) fence_mbar_init();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_b);
@@ -434,6 +433,17 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   pdl_wait();           // everything above overlapped the previous kernel's tail
+
+  if (p.pf_bytes > 0 && threadIdx.x == 64) {
+    // L2 prefetch of this CTA's slice of the hinted range (the next layer's weights), in 32 KB requests
+    const long long per = ((p.pf_bytes + gridDim.x - 1) / gridDim.x + 127) & ~127ll;
+    const long long lo = (long long)blockIdx.x * per;
+    const long long hi = lo + per < p.pf_bytes ? lo + per : p.pf_bytes;
+    for (long long off = lo; off < hi; off += 32768) {
+      const uint32_t sz = (uint32_t)(hi - off < 32768 ? hi - off : 32768);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf_ptr + off), "r"(sz) : "memory");
+    }
+  }
 
   // work item = (tile, k-split); splits of one tile are adjacent items, i.e. run on different CTAs
   const int nsplit = SPLITK ? p.splits : 1;
@@ -1399,6 +1409,13 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
   }
 
   p.dbg = g_igemm_dbg;
+  p.pf_ptr = nullptr;
+  p.pf_bytes = 0;
+  if (d->prefetch_ptr != nullptr && d->prefetch_bytes >= 16 && reinterpret_cast<uintptr_t>(d->prefetch_ptr) % 16 == 0) {
+    p.pf_ptr = reinterpret_cast<const uint8_t*>(d->prefetch_ptr);
+    p.pf_bytes = d->prefetch_bytes & ~15ll;
+    if (p.pf_bytes > (64ll << 20)) p.pf_bytes = 64ll << 20;          // half of the L2 at most
+  }
   p.gn_acc = nullptr;
   d->gn_fused_out = 0;
   if (d->gn_acc != nullptr && d->impl != 1 && !pair) {

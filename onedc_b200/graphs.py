@@ -107,11 +107,24 @@ class GraphedDecoder:
     def _capture(self):
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream())
+        traces = []
         with torch.cuda.stream(s), torch.no_grad():
             for seg in self._segments():
-                seg()
+                ops.WEIGHT_TRACE = []
+                try:
+                    seg()
+                finally:
+                    traces.append(ops.WEIGHT_TRACE)
+                    ops.WEIGHT_TRACE = None
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        # the last launch of a main-path segment hints the first weights of the next one (the four host rANS calls
+        # sit in between: the prefetch runs under them); the semantic segment (index 4) is its own chain
+        order = [0, 1, 2, 3, 5]
+        for a, b in zip(order[:-1], order[1:]):
+            nxt = next((w for w in traces[b] if w[1] > 0), None)
+            if nxt is not None:
+                traces[a] = traces[a] + [nxt]
         from . import lib
         pool = torch.cuda.graph_pool_handle()
         self.graphs = []
@@ -120,8 +133,12 @@ class GraphedDecoder:
         with torch.no_grad():                          # must never alias their (recycled) temporaries
             for i, seg in enumerate(self._segments()):
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=sem_pool if i == 4 else pool):
-                    seg()
+                ops.WEIGHT_PLAY = [traces[i], 0]
+                try:
+                    with torch.cuda.graph(g, pool=sem_pool if i == 4 else pool):
+                        seg()
+                finally:
+                    ops.WEIGHT_PLAY = None
                 self.graphs.append(g)
         self.launches = lib.launch_count() - n0
         torch.cuda.synchronize()
@@ -132,12 +149,20 @@ class GraphedDecoder:
         from . import lib
         assert self.lane_base == 0, "the resident leg is only captured on the default lanes"
         with torch.no_grad():
-            self.model.decode_resident(self.z_dev, self.syms_res)
+            ops.WEIGHT_TRACE = []
+            try:
+                self.model.decode_resident(self.z_dev, self.syms_res)
+            finally:
+                trace, ops.WEIGHT_TRACE = ops.WEIGHT_TRACE, None
             torch.cuda.synchronize()
             n0 = lib.launch_count()
             self.g_res = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_res):
-                self.img_res = self.model.decode_resident(self.z_dev, self.syms_res)
+            ops.WEIGHT_PLAY = [trace, 0]
+            try:
+                with torch.cuda.graph(self.g_res):
+                    self.img_res = self.model.decode_resident(self.z_dev, self.syms_res)
+            finally:
+                ops.WEIGHT_PLAY = None
             self.launches_res = lib.launch_count() - n0      # kernels of this library inside one replay
         torch.cuda.synchronize()
 

@@ -19,6 +19,12 @@ ATTN = os.environ.get("ONEDC_ATTN", "flash")
 PROFILE = None
 # when PROFILE is on and this is a list, igemm appends one shape record per launch (tools/layer_table.py)
 PROFILE_INFO = None
+# L2 prefetch of the next layer's weights.  The launch sequence of a decode is fixed, so the eager warm-up pass that
+# precedes every graph capture records the weight ranges in launch order (WEIGHT_TRACE = list) and the capture pass
+# plays them back (WEIGHT_PLAY = [trace, next index]): launch i carries the range of launch i + 1 as a prefetch hint.
+WEIGHT_TRACE = None
+WEIGHT_PLAY = None
+WEIGHT_PREFETCH = os.environ.get("ONEDC_WEIGHT_PREFETCH", "1") == "1"
 # bench-only: names of ops whose launches are skipped (outputs left uninitialised) so that the time of one kernel
 # family inside the graph-replayed step can be measured as a difference of two replays
 SKIP = set()
@@ -244,6 +250,17 @@ def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None
         PROFILE.append(("igemm_bytes", None, None, abytes))
     if "igemm" in SKIP:
         d.impl = 2                                   # dry run: same decisions (tiling, split-K, fused statistics), no launch
+    wrange = (wt.w.data_ptr(), wt.w.numel() * 2) if isinstance(wt, ConvW) else (0, 0)
+    if WEIGHT_TRACE is not None:
+        WEIGHT_TRACE.append(wrange)
+    if WEIGHT_PLAY is not None and WEIGHT_PREFETCH:
+        trace, i = WEIGHT_PLAY
+        if i < len(trace) and trace[i] == wrange:
+            if i + 1 < len(trace) and trace[i + 1][1] > 0:
+                d.prefetch_ptr, d.prefetch_bytes = trace[i + 1]
+            WEIGHT_PLAY[1] = i + 1
+        else:
+            WEIGHT_PLAY[1] = len(trace)                  # sequence differs from the recorded one: stop hinting
     if PROFILE_INFO is not None:
         PROFILE_INFO.append(dict(n=n, h=h, w=w, cin=c0 + c1, cout=d.cout, taps=d.ntaps if d.ntaps > 0 else d.ksize * d.ksize,
                                  stride=stride, epi=d.epi_mode, store=store, res=res is not None, f32=out.dtype == torch.float32))
