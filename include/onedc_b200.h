@@ -184,6 +184,11 @@ int onedc_window_merge(const void* attn_out, const void* residual, void* out, in
                        int32_t c, int32_t win, void* stream);
 /* x0 = (reduced - sqrt(1-a) eps)/sqrt(a) in fp32, then /0.18215 and post_quant_conv (4x4 + bias);
  * writes bf16 NHWC with 8 channels: [hi(4), lo(4)] split of the fp32 value; x0_out (fp32, optional) */
+/* second half of a 3x3 convolution with 1..4 output channels run as a 1x1 GEMM with 9*cout tap-expanded columns:
+   out[n,y,x,c] = bias[c] + res[n,y,x,c] + sum_t y[n, y+dy_t, x+dx_t, t*cout + c]; y fp32 NHWC with ldy columns, out fp32
+   NHWC (row pitch out_ld) or planar [n][cout][h*w] */
+int onedc_tap_gather(const float* y, int32_t ldy, int32_t cout, const float* bias, const float* res, int64_t res_ld,
+                     float* out, int64_t out_ld, int32_t planar, int32_t n_img, int32_t h, int32_t w, void* stream);
 int onedc_x0_prepare(const float* reduced, const float* eps, float sqrt_alpha, float sqrt_one_minus_alpha,
                      float inv_scaling, const float* pq_w, const float* pq_b, void* out_hilo, float* x0_out,
                      int64_t pixels, void* stream);

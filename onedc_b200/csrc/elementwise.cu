@@ -361,6 +361,48 @@ __global__ void x0_prepare_kernel(const float4* reduced, const float4* eps, floa
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 3x3 convolutions with a handful of output channels (UNet conv_out / vae_reduction 320 -> 4, VAE conv_out 128 -> 3)
+// waste the tensor core as an N = 16 implicit GEMM that re-reads the activations nine times (25 TFLOP/s).  They run
+// instead as ONE 1x1 GEMM with N = 9 * cout "tap-expanded" columns (activations read once) followed by this gather:
+//   out[n, y, x, c] = bias[c] + res[n, y, x, c] + sum_t Y[n, y + dy_t, x + dx_t, t * cout + c]      (zero padding)
+// Y fp32 [n, h, w, ldy]; out fp32, NHWC with row pitch out_ld or planar [n][c][h*w].  Thread = output pixel.
+template <int COUT>
+__global__ void __launch_bounds__(256) tap_gather_kernel(const float* __restrict__ Y, int ldy, const float* __restrict__ bias,
+                                                         const float* __restrict__ res, long long res_ld, float* __restrict__ out,
+                                                         long long out_ld, int planar, int n_img, int h, int w) {
+  pdl_wait();
+  const long long hw = (long long)h * w, total = hw * n_img;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(i / hw);
+    const int p = (int)(i - (long long)img * hw);
+    const int y = p / w, x = p - y * w;
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; c++) acc[c] = bias != nullptr ? __ldg(bias + c) : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+        const float* src = Y + ((long long)img * hw + (long long)yy * w + xx) * ldy + t * COUT;
+#pragma unroll
+        for (int c = 0; c < COUT; c++) acc[c] += __ldcg(src + c);
+      }
+    }
+    if (res != nullptr) {
+#pragma unroll
+      for (int c = 0; c < COUT; c++) acc[c] += __ldg(res + i * res_ld + c);
+    }
+    if (planar) {
+#pragma unroll
+      for (int c = 0; c < COUT; c++) out[((long long)img * COUT + c) * hw + p] = acc[c];
+    } else {
+#pragma unroll
+      for (int c = 0; c < COUT; c++) out[i * out_ld + c] = acc[c];
+    }
+  }
+}
+
 static inline int ew_blocks(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   const long long cap = (long long)sm_count() * 16;
@@ -478,6 +520,22 @@ extern "C" int onedc_x0_prepare(const float* reduced, const float* eps, float sq
   ONEDC_CUDA(launch_k(x0_prepare_kernel, ew_blocks(pixels, 256), 256, 0, (cudaStream_t)stream, (const float4*)reduced, (const float4*)eps,
                                                                              sqrt_alpha, sqrt_one_minus_alpha, inv_scaling,
                                                                              pq, (uint4*)out_hilo, (float4*)x0_out, pixels));
+  ONEDC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int onedc_tap_gather(const float* y, int32_t ldy, int32_t cout, const float* bias, const float* res, int64_t res_ld,
+                                float* out, int64_t out_ld, int32_t planar, int32_t n_img, int32_t h, int32_t w, void* stream) {
+  ONEDC_CHECK(cout >= 1 && cout <= 4 && ldy >= 9 * cout && (long long)h * w < (1ll << 31), "tap_gather: cout must be 1..4");
+  const long long total = (long long)n_img * h * w;
+  const int blocks = ew_blocks(total, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (cout) {
+    case 1: ONEDC_CUDA(launch_k(tap_gather_kernel<1>, blocks, 256, 0, st, y, ldy, bias, res, res_ld, out, out_ld, planar, n_img, h, w)); break;
+    case 2: ONEDC_CUDA(launch_k(tap_gather_kernel<2>, blocks, 256, 0, st, y, ldy, bias, res, res_ld, out, out_ld, planar, n_img, h, w)); break;
+    case 3: ONEDC_CUDA(launch_k(tap_gather_kernel<3>, blocks, 256, 0, st, y, ldy, bias, res, res_ld, out, out_ld, planar, n_img, h, w)); break;
+    default: ONEDC_CUDA(launch_k(tap_gather_kernel<4>, blocks, 256, 0, st, y, ldy, bias, res, res_ld, out, out_ld, planar, n_img, h, w)); break;
+  }
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }

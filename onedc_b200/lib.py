@@ -51,6 +51,7 @@ PROTOTYPES = {
     "onedc_groupnorm_stats": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "onedc_groupnorm_apply": (C.c_int, [_vp, _i32, _i64, _vp, _i32, _i64, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _i32, _f32,
                                         _vp, _vp, _i32, _vp, _i64, _vp]),
+    "onedc_tap_gather": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp]),
     "onedc_layernorm": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _i64, _vp]),
     "onedc_softmax_rows": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _f32, _vp, _i64, _vp]),
     "onedc_softmax_rows_batched": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _i32, _f32, _vp, _i64, _vp]),

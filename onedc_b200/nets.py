@@ -16,7 +16,7 @@ import math
 import torch
 
 from . import ops
-from .ops import (ACT_LRELU, ACT_NONE, ConvW, DepthwiseW, GroupNorm, LayerNorm, UpConv, igemm, pair_permute,
+from .ops import (ACT_LRELU, ACT_NONE, ConvW, DepthwiseW, GroupNorm, LayerNorm, TapConv3x3, UpConv, igemm, pair_permute,
                   pixshuf_permute)
 from .lib import EPI_GEGLU, EPI_PAIR_LRELU, ST_PIXSHUF, ST_TRANSPOSED
 from .weights import merge_lora
@@ -340,12 +340,12 @@ class UNet:
                 blk["up"] = UpConv(*_wb(sd, f"up_blocks.{i}.upsamplers.0.conv"), dev)
             self.up.append(blk)
         self.norm_out = GroupNorm(sd["conv_norm_out.weight"], sd["conv_norm_out.bias"], 1e-5, device=dev)
-        self.conv_out = ConvW(*_wb(sd, "conv_out"), dev)
+        self.conv_out = TapConv3x3(*_wb(sd, "conv_out"), dev)
         p = "vae_reduction."
         self.vr_n1 = GroupNorm(sd[p + "blocks.0.weight"], sd[p + "blocks.0.bias"], 1e-6, device=dev)
         self.vr_c1 = ConvW(*_wb(sd, p + "blocks.2"), dev)
         self.vr_n2 = GroupNorm(sd[p + "blocks.3.weight"], sd[p + "blocks.3.bias"], 1e-6, device=dev)
-        self.vr_c2 = ConvW(*_wb(sd, p + "blocks.5"), dev)
+        self.vr_c2 = TapConv3x3(*_wb(sd, p + "blocks.5"), dev)
         self.vr_sc = ConvW(*_wb(sd, p + "short_cut"), dev)
 
     def __call__(self, x, ctx):
@@ -353,7 +353,7 @@ class UNet:
         # vae_reduction (fp32 outputs: this feeds the x0 formula, amplified by 1/sqrt(alpha_bar) ~ 14.6)
         sc = igemm(x, self.vr_sc, out_dtype=f32)
         r = igemm(self.vr_n1(x), self.vr_c1, stats=True)
-        reduced = igemm(self.vr_n2(r), self.vr_c2, res=sc, out_dtype=f32)
+        reduced = self.vr_c2(self.vr_n2(r), res=sc)
         h = igemm(x, self.conv_in, stats=True)
         stack = [h]
         for blk in self.down:
@@ -375,7 +375,7 @@ class UNet:
                     h = blk["attn"][j](h, ctx)
             if "up" in blk:
                 h = blk["up"](h)
-        eps = igemm(self.norm_out(h), self.conv_out, out_dtype=f32)
+        eps = self.conv_out(self.norm_out(h))
         return eps, reduced
 
 
@@ -461,7 +461,7 @@ class VAEDecoder:
             up = UpConv(*_wb(sd, f"{d}.up_blocks.{i}.upsamplers.0.conv"), dev) if i < 3 else None
             self.ups.append((res, up))
         self.norm_out = GroupNorm(sd[d + ".conv_norm_out.weight"], sd[d + ".conv_norm_out.bias"], 1e-6, device=dev)
-        self.conv_out = ConvW(*_wb(sd, d + ".conv_out"), dev)
+        self.conv_out = TapConv3x3(*_wb(sd, d + ".conv_out"), dev)
         self.pq_w = sd["post_quant_conv.weight"].float().reshape(4, 4)
         self.pq_b = sd["post_quant_conv.bias"].float()
 
@@ -477,5 +477,5 @@ class VAEDecoder:
             if up is not None:
                 t = up(t)
         # NCHW fp32 image straight out of the last conv's epilogue
-        img = igemm(self.norm_out(t), self.conv_out, store=ST_TRANSPOSED, out_dtype=torch.float32)
+        img = self.conv_out(self.norm_out(t), planar=True)
         return img.view(n, 3, 8 * h, 8 * w)

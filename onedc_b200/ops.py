@@ -137,6 +137,37 @@ class UpConv:
         return out
 
 
+class TapConv3x3:
+    """3x3 conv (stride 1, zero padding) with <= 4 output channels and fp32 output: one 1x1 GEMM with 9*cout
+    tap-expanded columns (column t*cout + c = tap t of output channel c), then onedc_tap_gather sums each pixel's nine
+    neighbours.  The activations are read once instead of nine times and no N = 16 padding tile is computed."""
+
+    def __init__(self, w, bias=None, device="cuda"):
+        cout, cin, k, _ = w.shape
+        assert k == 3 and cout <= 4
+        self.cout = cout
+        wexp = w.float().permute(2, 3, 0, 1).reshape(9 * cout, cin)              # [(ky*3+kx)*cout + c, cin]
+        pad = (-9 * cout) % 16
+        if pad:
+            wexp = torch.cat([wexp, torch.zeros(pad, cin)], 0)
+        self.gemm = ConvW(wexp.contiguous(), None, device)
+        self.bias = None if bias is None else bias.detach().float().contiguous().to(device)
+
+    def __call__(self, x, res=None, planar=False):
+        n, h, w, _ = x.shape
+        y = igemm(x, self.gemm, out_dtype=torch.float32)                          # [n, h, w, 9*cout (padded)]
+        if planar:
+            out = torch.empty((n, self.cout, h * w), device=x.device, dtype=torch.float32)
+        else:
+            out = torch.empty((n, h, w, self.cout), device=x.device, dtype=torch.float32)
+        if res is not None:
+            assert res.dtype == torch.float32 and res.shape == (n, h, w, self.cout) and res.is_contiguous()
+        L.check(L.load().onedc_tap_gather(y.data_ptr(), y.shape[-1], self.cout, 0 if self.bias is None else self.bias.data_ptr(),
+                                          0 if res is None else res.data_ptr(), self.cout, out.data_ptr(), self.cout,
+                                          1 if planar else 0, n, h, w, _stream()), "tap_gather")
+        return out
+
+
 def pair_permute(w, b, bn=256):
     """Reorders output channels so that every N tile of `bn` GEMM columns holds bn/2 channels of the first
     half followed by the matching bn/2 channels of the second half (ConvFFN3 / GEGLU epilogues)."""

@@ -256,3 +256,26 @@ def test_transposed_column_copy_mode(cuda, n, h, w, cin, cout, two, f32):
     o = out.float().view(n, h * w, ng, cout // ng)
     want = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1).double()
     assert torch.allclose(got, want, rtol=3e-3, atol=1e-4 * float(want.abs().max()))
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,planar,with_res", [(1, 96, 96, 320, 4, False, True), (2, 40, 56, 128, 3, True, False),
+                                                          (1, 33, 17, 64, 4, False, False), (1, 128, 128, 128, 3, True, False)])
+def test_tap_expanded_small_cout_conv(cuda, n, h, w, cin, cout, planar, with_res):
+    """3x3 convs with 3-4 output channels run as a 1x1 GEMM over 9*cout tap-expanded columns + a 9-neighbour gather
+    (ops.TapConv3x3): same result as the fp32 torch convolution of the bf16-rounded operands, zero padding included."""
+    from onedc_b200 import ops
+    x = _mk((n, h, w, cin), cuda, 1)
+    wt = _mk((cout, cin, 3, 3), "cpu", 2, scale=(cin * 9) ** -0.5).float()
+    b = _mk((cout,), "cpu", 3).float()
+    res = torch.randn((n, h, w, cout), generator=torch.Generator().manual_seed(4)).to(cuda) if with_res else None
+    tc = ops.TapConv3x3(wt, b, cuda)
+    out = tc(x, res=res, planar=planar)
+    ref = _ref_conv(x, wt.to(torch.bfloat16).float().to(cuda), b.to(cuda), 3, 1)
+    if with_res:
+        ref = ref + res
+    if planar:
+        assert out.shape == (n, cout, h * w)
+        out = out.view(n, cout, h, w).permute(0, 2, 3, 1)
+    assert out.dtype == torch.float32
+    _close(out, ref, tol=2e-3)
+    assert torch.equal(tc(x, res=res, planar=planar).reshape(-1), (out if not planar else out.permute(0, 3, 1, 2)).reshape(-1))
