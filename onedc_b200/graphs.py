@@ -79,6 +79,9 @@ class GraphedDecoder:
             self.y_sem = c.semantic_adaptor(z_sem)
             self.cat = c.dec.alloc_cat(self.B, self.h16, self.w16, self.dev)
             c.dec.sem_path(self.y_sem, self.cat)
+            # the UNet's 16 cross-attention K | V projections depend on the hyperprior tokens only
+            b, hz, wz, cs = self.y_sem.shape
+            self.ctx_kv = self.model.feedforward_model.project_ctx(self.y_sem.reshape(b, hz * wz, cs))
         finally:
             ops.SCRATCH_LANE = self.lane_base
 
@@ -87,7 +90,7 @@ class GraphedDecoder:
         self.sym_dev.view(self.B, self.nsym).copy_(self.sym_host, non_blocking=True)
         ops.dequant_accum(self.sym_dev, self.sm[3][..., 128:], self.params[..., :128], 3)
         x_hat = c.dec.main_path(self.params[..., :128], self.cat)
-        self.img_dev = self.model.generate(x_hat, self.y_sem)
+        self.img_dev = self.model.generate(x_hat, self.y_sem, ctx_kv=self.ctx_kv)
         self.img_host.copy_(self.img_dev, non_blocking=True)
 
     def _segments(self):

@@ -52,11 +52,11 @@ class SD15_1step_codec_stage1:
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def generate(self, x_hat, y_sem, stages=None):
+    def generate(self, x_hat, y_sem, stages=None, ctx_kv=None):
         """x_hat [B,h8,w8,320], y_sem [B,hz,wz,768] (NHWC bf16) -> padded image fp32 [B,3,H,W]."""
         b, hz, wz, cs = y_sem.shape
         ctx = y_sem.reshape(b, hz * wz, cs)                 # 'b c h w -> b (h w) c' is a no-op in NHWC
-        eps, reduced = self.feedforward_model(x_hat, ctx)
+        eps, reduced = self.feedforward_model(x_hat, ctx, ctx_kv)     # ctx_kv: precomputed cross-attention K | V
         z, x0 = ops.x0_prepare(reduced, eps, self.sqrt_alpha, self.sqrt_1m_alpha, 1.0 / VAE_SCALING,
                                self.vae_large.pq_w, self.vae_large.pq_b, want_x0=stages is not None)
         img = self.vae_large(z)

@@ -279,7 +279,13 @@ class UNetTransformer:
             ops.attention_unfused(q, k, vT, o, self.heads, self.d)
         return o
 
-    def __call__(self, x, ctx):
+    def project_ctx(self, ctx):
+        """K | V of the cross attention: depends on the hyperprior tokens only, so it can be computed ahead of the UNet
+        (GraphedDecoder does it on the semantic side stream, under the host rANS)."""
+        b, Lc, cc = ctx.shape
+        return igemm(ctx.view(b, 1, Lc, cc), self.kv2).view(b, Lc, 2 * self.c)
+
+    def __call__(self, x, ctx, kv=None):
         b, h, w, c = x.shape
         s = h * w
         t = igemm(self.norm(x, silu=False), self.proj_in).view(b, s, c)
@@ -292,7 +298,8 @@ class UNetTransformer:
         n2 = self.ln2(t)
         q = igemm(n2.view(b, 1, s, c), self.q2).view(b, s, c)
         Lc = ctx.shape[1]
-        kv = igemm(ctx.view(b, 1, Lc, ctx.shape[2]), self.kv2).view(b, Lc, 2 * c)
+        if kv is None:
+            kv = self.project_ctx(ctx)
         o = self._attend(q, kv[:, :, :c], kv[:, :, c:], ctx.view(b, 1, Lc, ctx.shape[2]), self.v2, b, s)
         t = igemm(o.view(b, 1, s, c), self.out2, res=t.view(b, 1, s, c)).view(b, s, c)
         # feed forward (GEGLU fused into the first GEMM's epilogue)
@@ -348,8 +355,24 @@ class UNet:
         self.vr_c2 = TapConv3x3(*_wb(sd, p + "blocks.5"), dev)
         self.vr_sc = ConvW(*_wb(sd, p + "short_cut"), dev)
 
-    def __call__(self, x, ctx):
+    def transformers(self):
+        """the 16 transformer blocks in call order"""
+        out = []
+        for blk in self.down:
+            out += blk.get("attn", [])
+        out.append(self.mid_attn)
+        for blk in self.up:
+            out += blk.get("attn", [])
+        return out
+
+    def project_ctx(self, ctx):
+        """cross-attention K | V of every transformer block (ctx-only work), in call order"""
+        return [t.project_ctx(ctx) for t in self.transformers()]
+
+    def __call__(self, x, ctx, kvs=None):
         f32 = torch.float32
+        kvs = iter(kvs) if kvs is not None else None
+        nkv = lambda: next(kvs) if kvs is not None else None
         # vae_reduction (fp32 outputs: this feeds the x0 formula, amplified by 1/sqrt(alpha_bar) ~ 14.6)
         sc = igemm(x, self.vr_sc, out_dtype=f32)
         r = igemm(self.vr_n1(x), self.vr_c1, stats=True)
@@ -360,19 +383,19 @@ class UNet:
             for j, r_ in enumerate(blk["res"]):
                 h = r_(h)
                 if "attn" in blk:
-                    h = blk["attn"][j](h, ctx)
+                    h = blk["attn"][j](h, ctx, nkv())
                 stack.append(h)
             if "down" in blk:
                 h = igemm(h, blk["down"], stride=2, stats=True)
                 stack.append(h)
         h = self.mid_res[0](h)
-        h = self.mid_attn(h, ctx)
+        h = self.mid_attn(h, ctx, nkv())
         h = self.mid_res[1](h)
         for blk in self.up:
             for j, r_ in enumerate(blk["res"]):
                 h = r_(h, stack.pop())
                 if "attn" in blk:
-                    h = blk["attn"][j](h, ctx)
+                    h = blk["attn"][j](h, ctx, nkv())
             if "up" in blk:
                 h = blk["up"](h)
         eps = self.conv_out(self.norm_out(h))
