@@ -12,6 +12,9 @@
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 softmax + output.  QK^T of block j+1 is
 // issued before P V of block j, so the tensor core works on the next scores while softmax runs; two CTAs
 // per SM (TMEM 256 columns each) overlap one CTA's softmax with the other's MMAs.
+// Launch plans (attention_plan / onedc_attention_set_plan): the default above; one S buffer + three CTAs per SM for
+// head_dim <= 64; the key range split over 2..4 CTAs per query tile with an fp32 merge pass (attention_merge_kernel).
+// The alternatives are measured slower on B200 for the UNet's shapes (numbers at attention_plan) and stay tested.
 //
 // The SIMT kernel at the bottom is the on-GPU checker (impl = 1), never used by the decode path.
 #include "../../include/onedc_b200.h"

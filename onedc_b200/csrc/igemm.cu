@@ -12,9 +12,17 @@
 // * MMA: tcgen05.mma cta_group::1 kind::f16, M = 128, N = BN (16..256), K = 16 per instruction, operands in
 //   128B-swizzled shared memory written by TMA, fp32 accumulators in TMEM (two buffers of 256 columns so the
 //   epilogue of tile i overlaps the main loop of tile i+1).
-// * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..5 =
-//   epilogue (tcgen05.ld -> bias/activation/pair-ops/residual -> global).  Persistent CTAs, static
-//   round-robin tile schedule.
+// * Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..9 =
+//   epilogue (tcgen05.ld -> bias/activation/pair-ops/residual -> global, fused GroupNorm statistics).  Persistent
+//   CTAs, static round-robin tile schedule.  Producer and issuer loops run on the whole warp with uniform state
+//   (see the comment at the role dispatch): single-lane scalar code was the first bound of this kernel.
+// * Three tilings, chosen per layer by the host (igemm_launch): the tap tile above; the column-copy tile (16 x 8
+//   pixels, ONE A box per tap column shared by its three taps, separate A / B rings) for stride-1 multi-tap convs
+//   that run several tiles per CTA; and its transposed form (weights as the M operand, 32 x 8 pixels as N = 256)
+//   for cout <= 128.  What bounds the big layers is shared-memory bandwidth (MMA operand reads + TMA writes,
+//   128 B/clk/SM), so the tilings differ in bytes moved per MMA clock: 192 / 170 / 149.  DESIGN.md section 8.
+// * Split-K (template SPLITK) for layers with too few tiles to fill the GPU: fp32 partial tiles parked in a
+//   coalesced layout, every CTA fetches its row slice of all splits with bulk copies and finishes it.
 //
 // The SIMT kernel at the bottom evaluates the same descriptor with scalar loops; it exists to check the
 // tensor-core kernel on the GPU (tests, impl = 1) and is never used by the decode path.
