@@ -133,11 +133,49 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def run_kodak64(args):
+    """BASELINE.json configs[2] (not the default bench line): 64 synthetic 768x512 (Kodak-shape) streams sharded
+    `i % world == rank` over the ranks, each rank decoding its shard through model.decode_many (host bytes -> host
+    images, `--pipeline` images in flight).  No collective on the path; time = max over ranks."""
+    import torch
+    from onedc_b200 import parallel
+    from onedc_b200.model import SD15_1step_codec_stage1
+    rank, world, local = parallel.init_distributed()
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    H, W, N = 512, 768, 64
+    model = SD15_1step_codec_stage1(state_dicts=_state_dicts(), device=dev)
+    model.codec_model.update(force=True)
+    mine = parallel.shard(list(range(N)), rank, world)
+    streams = [model.codec_model.compress_synthetic(H, W, seed=1234 + i)[0] for i in mine]
+    depth = max(args.pipeline, 1)
+    model.decode_many(streams[: 2 * depth], depth=depth)            # capture + warm-up
+    reps = []
+    for _ in range(max(args.steps // 4, 2)):
+        parallel.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        imgs = model.decode_many(streams, depth=depth)
+        torch.cuda.synchronize()
+        reps.append(parallel.reduce_max(time.perf_counter() - t0))
+    assert len(imgs) == len(mine) and imgs[0].shape == (1, 3, H, W)
+    t = sorted(reps)[len(reps) // 2]
+    if rank == 0:
+        print(json.dumps({"metric": "768x512 batch-64 decode throughput", "value": N * H * W * MP / t, "unit": "MP/s",
+                          "n_gpus": world, "ms_per_image": t * 1e3 / N, "images": N, "higher_is_better": True,
+                          "scaling": "strong", "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": "OneDC decode of 64 synthetic 768x512 streams sharded over the ranks "
+                                                 "(BASELINE.json configs[2]), host bytes -> host images",
+                                     "images_in_flight_per_gpu": depth, "repeats": len(reps)}}))
+
+
 def run_ours(args):
     import torch
     from onedc_b200 import bitstream, lib, ops, parallel
     from onedc_b200.model import SD15_1step_codec_stage1
 
+    if args.workload == "kodak64":
+        return run_kodak64(args)
     rank, world, local = parallel.init_distributed()
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
@@ -341,6 +379,8 @@ def main():
     ap.add_argument("--ref-size", type=int, default=0, help="side of the CPU sample image; 0 = largest that fits the time budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipeline", type=int, default=3, help="images in flight for the extra e2e_pipelined figure (0/1 = skip)")
+    ap.add_argument("--workload", default="single768", choices=["single768", "kodak64"],
+                    help="single768 = the headline line (configs[1]); kodak64 = 64 x 768x512 streams sharded over the ranks")
     ap.add_argument("--eager", action="store_true", help="launch kernels from Python instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
