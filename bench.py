@@ -10,6 +10,11 @@ bf16, 1xB200) of synthetic streams made by the codec's own encode twin with seed
   e2e   : model.decode(stream=bytes) from host bytes to a host (pinned) image, host rANS and all H2D/D2H inside.
 Images are independent: ranks decode different streams, no collective on the path ("weak" scaling); time is
 barrier + synchronize bracketed and the max over ranks.
+
+After the headline region the same JSON line gets one entry per remaining BASELINE.json configuration under
+"configs": kodak64 (configs[2], 64 x 768x512 streams sharded over the ranks: strong scaling), z_only_768 (configs[3]),
+s2048 (configs[4], with the igemm / attention split), and the CPU figures of configs[0] (256x256, all threads and one
+thread) inside "cpu_baseline".  `--no-extras` skips them.
 """
 import argparse
 import json
@@ -78,95 +83,200 @@ def _state_dicts():
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def _oracle_and_size(args, budget_s):
-    """Builds the CPU oracle and picks the largest square sample (768 = the workload itself, else 512 / 256) whose
-    `budget_s` seconds of decodes fit; decode time scales with the pixel count."""
+WORKLOAD = "OneDC decode of 1 synthetic 768x768 image per step (BASELINE.json configs[1]), random-init weights seed 0"
+
+
+def _oracle(threads=None):
     import torch
     from oracle.decode import OneDCOracle
-    cores = os.cpu_count() or 1
+    cores = threads or os.cpu_count() or 1
     torch.set_num_threads(cores)
     sds = _state_dicts()
-    orc = OneDCOracle(sds[1], sds[0], sds[2])
-    s256, _, _ = orc.codec.make_stream(256, 256, seed=1234)
-    orc.decode(s256)                                   # warm-up (thread pools, allocator)
-    t0 = time.perf_counter()
-    orc.decode(s256)
-    t256 = time.perf_counter() - t0
-    side = args.ref_size
-    if side <= 0:
-        side = 256
-        for cand in (768, 512):
-            if t256 * (cand / 256.0) ** 2 * budget_s[0] <= budget_s[1]:
-                side = cand
-                break
-    return orc, cores, side, t256
+    return OneDCOracle(sds[1], sds[0], sds[2]), cores
+
+
+def _time_decodes(orc, stream, n):
+    ts = []
+    for _ in range(n):
+        t0 = time.perf_counter()
+        orc.decode(stream)
+        ts.append(time.perf_counter() - t0)
+    return ts
 
 
 def run_reference(args):
     """The reference's CPU implementation of the path: the oracle port (kind "port": the reference's UNet/VAE live
-    in diffusers/peft which are not installable here, so the reference itself cannot run), fp32, all host threads.
-    Each step decodes one synthetic image of the workload's size when K + W such decodes fit ~2.5 minutes, else a
-    smaller bounded sample; MP/s is size-normalised."""
+    in diffusers/peft which are not installable here, so the reference itself cannot run; the port is pinned to the
+    reference source by tests/test_reference_pin_cpu.py), fp32, all host threads.  Every step decodes one synthetic image
+    of the workload's own size, 768x768 -- never a smaller sample.  If K + W such decodes would not fit ~4 minutes on this
+    box, fewer decodes are timed (at least 3) and the line says how many."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    orc, cores, side, t256 = _oracle_and_size(args, (args.steps + args.warmup, 150.0))
+    side = args.size
+    orc, cores = _oracle()
     stream, _, _ = orc.codec.make_stream(side, side, seed=1234)
-    for _ in range(args.warmup):
-        orc.decode(stream)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        orc.decode(stream)
-    dt = (time.perf_counter() - t0) / args.steps
+    t_first = _time_decodes(orc, stream, 1)[0]                      # doubles as the first warm-up decode
+    budget = 240.0
+    warm = max(0, min(args.warmup - 1, int(0.15 * budget / t_first)))
+    _time_decodes(orc, stream, warm)
+    timed = max(3, min(args.steps, int((budget - (warm + 1) * t_first) / t_first)))
+    ts = _time_decodes(orc, stream, timed)
+    dt = sum(ts) / len(ts)
     v = side * side * MP / dt
-    sample = f"{args.steps} x one synthetic {side}x{side} stream (full decode path incl. rANS), fp32 torch CPU"
+    sample = (f"{timed} timed + {warm + 1} warm-up decodes of one synthetic {side}x{side} stream (full decode path incl. rANS), "
+              f"fp32 torch CPU, {cores} threads" + ("" if timed == args.steps else f"; {args.steps} steps requested, "
+              f"{timed} fit the {budget:.0f} s budget"))
     print(json.dumps({
         "impl": "reference", "metric": "768x768 decode throughput", "value": v, "unit": "MP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"OneDC decode of 1 synthetic {side}x{side} image per step"
-                               + ("" if side == 768 else " (bounded sample of the 768x768 workload)")
-                               + ", random-init weights seed 0, host CPU"},
+        "config": {"workload": WORKLOAD if side == 768 else f"OneDC decode of 1 synthetic {side}x{side} image per step",
+                   "execution": "host CPU, torch fp32", "timed_decodes": timed},
+        "p50_ms_per_image_e2e": sorted(ts)[len(ts) // 2] * 1e3,
         "cpu_baseline": {"value": v, "unit": "MP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def kodak64(model, parallel, args, reps=None):
+    """BASELINE.json configs[2]: 64 synthetic 768x512 (Kodak-shape) streams sharded `i % world == rank` over the ranks,
+    each rank decoding its shard through model.decode_many (host bytes -> host images, `--pipeline` images in flight).
+    No collective on the path; time = max over ranks; the work is fixed as N grows (strong scaling)."""
+    import torch
+    rank, world = parallel.rank_world()
+    H, W, N = 512, 768, 64
+    mine = parallel.shard(list(range(N)), rank, world)
+    streams = [model.codec_model.compress_synthetic(H, W, seed=1234 + i)[0] for i in mine]
+    depth = max(args.pipeline, 1)
+    model.decode_many(streams[: 2 * depth], depth=depth)            # capture + warm-up
+    times = []
+    for _ in range(reps or max(args.steps // 4, 2)):
+        parallel.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        imgs = model.decode_many(streams, depth=depth)
+        torch.cuda.synchronize()
+        times.append(parallel.reduce_max(time.perf_counter() - t0))
+    assert len(imgs) == len(mine) and imgs[0].shape == (1, 3, H, W)
+    t = sorted(times)[len(times) // 2]
+    return {"metric": "768x512 batch-64 decode throughput", "value": N * H * W * MP / t, "unit": "MP/s",
+            "n_gpus": world, "ms_per_image": t * 1e3 / N, "images": N, "higher_is_better": True,
+            "scaling": "strong", "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "OneDC decode of 64 synthetic 768x512 streams sharded over the ranks "
+                                   "(BASELINE.json configs[2]), host bytes -> host images",
+                       "images_in_flight_per_gpu": depth, "repeats": len(times)}}
+
+
 def run_kodak64(args):
-    """BASELINE.json configs[2] (not the default bench line): 64 synthetic 768x512 (Kodak-shape) streams sharded
-    `i % world == rank` over the ranks, each rank decoding its shard through model.decode_many (host bytes -> host
-    images, `--pipeline` images in flight).  No collective on the path; time = max over ranks."""
     import torch
     from onedc_b200 import parallel
     from onedc_b200.model import SD15_1step_codec_stage1
     rank, world, local = parallel.init_distributed()
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
-    H, W, N = 512, 768, 64
     model = SD15_1step_codec_stage1(state_dicts=_state_dicts(), device=dev)
     model.codec_model.update(force=True)
-    mine = parallel.shard(list(range(N)), rank, world)
-    streams = [model.codec_model.compress_synthetic(H, W, seed=1234 + i)[0] for i in mine]
-    depth = max(args.pipeline, 1)
-    model.decode_many(streams[: 2 * depth], depth=depth)            # capture + warm-up
-    reps = []
-    for _ in range(max(args.steps // 4, 2)):
-        parallel.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        imgs = model.decode_many(streams, depth=depth)
-        torch.cuda.synchronize()
-        reps.append(parallel.reduce_max(time.perf_counter() - t0))
-    assert len(imgs) == len(mine) and imgs[0].shape == (1, 3, H, W)
-    t = sorted(reps)[len(reps) // 2]
+    res = kodak64(model, parallel, args)
     if rank == 0:
-        print(json.dumps({"metric": "768x512 batch-64 decode throughput", "value": N * H * W * MP / t, "unit": "MP/s",
-                          "n_gpus": world, "ms_per_image": t * 1e3 / N, "images": N, "higher_is_better": True,
-                          "scaling": "strong", "dtype": "bf16", "data": "synthetic",
-                          "config": {"workload": "OneDC decode of 64 synthetic 768x512 streams sharded over the ranks "
-                                                 "(BASELINE.json configs[2]), host bytes -> host images",
-                                     "images_in_flight_per_gpu": depth, "repeats": len(reps)}}))
+        print(json.dumps(res))
+
+
+def _event_time(fn, k):
+    import torch
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(k):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / k
+
+
+def _pct(xs, q):
+    xs = sorted(xs)
+    return xs[min(len(xs) - 1, int(round(q * (len(xs) - 1))))]
+
+
+def z_only_768(model, parallel, args):
+    """BASELINE.json configs[3]: hyperprior-only (0.0034 bpp) decode of 768x768 -- 144 random 14-bit indices, no y stream,
+    no rANS (models/sd15_onedc_codec_z_only).  resident: indices in HBM, one graph replay; e2e: model.decode_z_only(host
+    indices) -> pinned host image."""
+    import torch
+    rank, world = parallel.rank_world()
+    H = W = 768
+    z = torch.randint(0, 16384, (1, 12, 12), generator=torch.Generator().manual_seed(5 + rank), dtype=torch.int32)
+    model.decode_z_only(z)                                          # capture + warm-up
+    gd = model.graphed(1, H, W)
+    for _ in range(3):
+        gd.run_z_only()
+    parallel.barrier()
+    t_res = parallel.reduce_max(_event_time(gd.run_z_only, args.steps) / 1e3)
+    lat = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        model.decode_z_only(z)
+        torch.cuda.current_stream().synchronize()
+        lat.append(time.perf_counter() - t0)
+    t_e2e = parallel.reduce_max(sum(lat) / len(lat))
+    return {"metric": "768x768 z-only decode throughput", "value": world * H * W * MP / t_res, "unit": "MP/s",
+            "ms_per_step": t_res * 1e3, "scaling": "weak", "gpu_launches_per_step": gd.launches_z,
+            "e2e": {"value": world * H * W * MP / t_e2e, "unit": "MP/s", "ms_per_step": t_e2e * 1e3,
+                    "p50_ms": _pct(lat, .5) * 1e3, "p90_ms": _pct(lat, .9) * 1e3,
+                    "h2d_bytes_per_step": 144 * 4, "d2h_bytes_per_step": 3 * H * W * 4},
+            "config": {"workload": "sd15_onedc_codec_z_only decode of one 768x768 image from 144 z indices "
+                                   "(BASELINE.json configs[3])"}}
+
+
+def s2048(model, parallel, args):
+    """BASELINE.json configs[4]: one synthetic 2048x2048 image (256x256 latent, S = 65 536 UNet self-attention) per GPU.
+    resident + e2e timings, and the igemm / attention split from per-launch CUDA events over one eager pass."""
+    import torch
+    from onedc_b200 import bitstream, ops
+    rank, world = parallel.rank_world()
+    H = W = 2048
+    stream = model.codec_model.compress_synthetic(H, W, seed=777 + rank)[0]
+    d = bitstream.decode_i(stream)
+    trace = []
+    z_idx = model.codec_model.parse_z([d["bit_stream_z"]], H, W)
+    model.codec_model._decompress_batch([d["bit_stream_y"]], [d["bit_stream_z"]], H, W, trace)
+    syms = [t["sym"].view(1, 32, H // 16, W // 16).to(model.device) for t in trace]
+    gd = model.graphed(1, H, W)
+    gd.set_resident_inputs(z_idx, syms)
+    gd.capture_resident()
+    for _ in range(2):
+        gd.run_resident()
+    steps = max(3, min(args.steps, 5))
+    parallel.barrier()
+    t_res = parallel.reduce_max(_event_time(gd.run_resident, steps) / 1e3)
+    model.decode(stream=stream)                                     # capture of the five-graph e2e route + warm-up
+    lat = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        model.decode(stream=stream)
+        torch.cuda.current_stream().synchronize()
+        lat.append(time.perf_counter() - t0)
+    t_e2e = parallel.reduce_max(sum(lat) / len(lat))
+    ops.PROFILE = []
+    model.decode_resident(z_idx, syms)
+    torch.cuda.synchronize()
+    prof, ops.PROFILE = ops.PROFILE, None
+    fam = {}
+    for name in ("igemm", "attention"):
+        ms = sum(a.elapsed_time(b) for n, a, b, f in prof if n == name)
+        fl = sum(f for n, a, b, f in prof if n == name)
+        fam[name] = {"ms_per_step_event_sum": ms, "gflop": fl / 1e9, "tflops": fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0,
+                     "launches": sum(1 for n, *_ in prof if n == name)}
+    nsym = 128 * (H // 16) * (W // 16)
+    return {"metric": "2048x2048 decode throughput", "value": world * H * W * MP / t_res, "unit": "MP/s",
+            "ms_per_step": t_res * 1e3, "steps": steps, "scaling": "weak (replicas: one image cannot be split, DESIGN.md 5)",
+            "e2e": {"value": world * H * W * MP / t_e2e, "unit": "MP/s", "ms_per_step": t_e2e * 1e3,
+                    "p50_ms": _pct(lat, .5) * 1e3, "h2d_bytes_per_step": nsym * 2 + 32 * 32 * 4,
+                    "d2h_bytes_per_step": nsym * 2 + 3 * H * W * 4, "host_rans_ms": gd.last_rans_ms},
+            "kernels": fam,
+            "config": {"workload": "OneDC decode of one synthetic 2048x2048 image per GPU (BASELINE.json configs[4])"}}
 
 
 def run_ours(args):
@@ -184,6 +294,7 @@ def run_ours(args):
     model = SD15_1step_codec_stage1(state_dicts=_state_dicts(), device=dev)
     model.codec_model.update(force=True)
     streams = [model.codec_model.compress_synthetic(H, W, seed=1234 + rank * 1000 + i)[0] for i in range(B)]
+    extras_on = not args.no_extras and B == 1 and H == 768 and not args.eager
     hdr = [bitstream.decode_i(s) for s in streams]
     # resident inputs for the `value` leg: decode once, keep z indices and the four symbol planes in HBM
     trace = []
@@ -269,26 +380,26 @@ def run_ours(args):
     #      without the igemm launches (every kernel's run time here is data independent).  Per-launch events over an
     #      eager step (launches queued behind a spin kernel so they run back to back) give the cross-check and the
     #      algorithmic FLOP / byte counts.
-    def timed(fn, k):
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(k):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / k
-
+    timed = _event_time
     ig_ms_diff = at_ms_diff = None
     if use_graphs:
+        # dry launches: bench.py swaps the product's launch routes for planning-only ones while a second graph is captured
+        # (ops.IMPL = 2 makes onedc_igemm take every decision -- tiling, split-K, fused statistics -- without launching;
+        # attention is skipped by patching the Python wrapper).  Nothing of this lives in the product path.
         from onedc_b200.graphs import GraphedDecoder
         t_full = timed(gd.run_resident, args.steps)
         for name in ("igemm", "attention"):
-            ops.SKIP = {name}
-            g2 = GraphedDecoder(model, B, H, W)
-            g2.set_resident_inputs(z_idx, syms)
-            g2.capture_resident()
-            ops.SKIP = set()
+            old_impl, old_attn = ops.IMPL, ops.attention
+            if name == "igemm":
+                ops.IMPL = 2
+            else:
+                ops.attention = lambda q, k, v, out, *a, **kw: out
+            try:
+                g2 = GraphedDecoder(model, B, H, W)
+                g2.set_resident_inputs(z_idx, syms)
+                g2.capture_resident()
+            finally:
+                ops.IMPL, ops.attention = old_impl, old_attn
             for _ in range(2):
                 g2.run_resident()
             dt = t_full - timed(g2.run_resident, args.steps)
@@ -296,6 +407,7 @@ def run_ours(args):
                 ig_ms_diff = dt
             else:
                 at_ms_diff = dt
+            g2.release()
             del g2
     ops.PROFILE = []
     torch.cuda._sleep(int(0.12 * 1.9e9))
@@ -312,20 +424,38 @@ def run_ours(args):
     at_ms = at_ms_diff if at_ms_diff is not None else at_ms_ev
     hbm, burst, sustained, src = _peaks()
     achieved = ig_fl / (ig_ms * 1e-3) / 1e12 if ig_ms > 0 else 0.0
-    traffic = None
+    # DRAM traffic is an ncu figure and cannot be measured inside an un-profiled run: it is read from the newest committed
+    # launch summary, and only if that summary was taken from the same launch sequence (same igemm launch count)
+    traffic, traffic_src = None, None
     try:
-        summ = json.load(open(os.path.join(ROOT, "profiles", "launch_summary_r1.json")))
-        traffic = sum(v["dram_MB"] for k, v in summ.items() if "igemm_tc" in k) * 1e6
+        import glob
+        for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "launch_summary_r*.json")), reverse=True):
+            summ = json.load(open(f))
+            ig = {k: v for k, v in summ.items() if "igemm_tc" in k}
+            if sum(v.get("launches", 0) for v in ig.values()) == n_ig:
+                traffic = sum(v["dram_MB"] for v in ig.values()) * 1e6
+                traffic_src = os.path.relpath(f, ROOT)
+                break
     except Exception:
         pass
+    # ---- the other BASELINE.json configurations (after the headline region; every rank takes part)
+    extras = {}
+    if extras_on:
+        for name, fn in (("z_only_768", z_only_768), ("kodak64", kodak64), ("s2048", s2048)):
+            try:
+                extras[name] = fn(model, parallel, args) if name != "kodak64" else kodak64(model, parallel, args, reps=2)
+            except Exception as e:                                   # a failed extra must not take the headline line down
+                extras[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            model.release_graphs()                                   # drop that size's graphs / pools before the next one
     if rank != 0:
         return
     pixels = H * W * B * world
     nsym = 128 * h16 * w16
     roof = {"bound": "tensor", "kernel": "igemm_tc_kernel", "achieved": achieved, "peak": sustained, "unit": "TFLOP/s",
             "frac": achieved / sustained, "traffic": traffic,
-            "traffic_note": "dram read+write bytes of all igemm launches of one step, ncu cold-cache capture "
-                            "(profiles/launch_summary_r1.json); algorithmic_bytes_per_step counts every operand once",
+            "traffic_note": ("dram read+write bytes of all igemm launches of one step, ncu cold-cache capture (" + traffic_src +
+                             "); algorithmic_bytes_per_step counts every operand once") if traffic_src else
+                            "no committed ncu launch summary matches this launch sequence: not measured",
             "peak_source": f"{src} (sustained; burst {burst})",
             "launches_per_step": n_ig, "kernel_ms_per_step": ig_ms, "kernel_ms_per_step_event_sum": ig_ms_ev,
             "algorithmic_gflop_per_step": ig_fl / 1e9, "algorithmic_bytes_per_step": ig_bytes,
@@ -336,10 +466,11 @@ def run_ours(args):
         "metric": "768x768 decode throughput", "value": pixels * MP / t_res, "unit": "MP/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_res * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"OneDC decode of {B} synthetic {H}x{W} image(s) per GPU per step (BASELINE.json configs[1]), "
-                               "random-init weights seed 0", "batch_per_gpu": B, "execution": "cuda-graph replay" if use_graphs else "eager launches", "parallelism": f"dp{world} (independent streams)",
+        "value_is": "device-resident leg (inputs in HBM, image left in HBM); e2e is the host-bytes -> host-image figure",
+        "config": {"workload": WORKLOAD if (B == 1 and H == 768) else
+                   f"OneDC decode of {B} synthetic {H}x{W} image(s) per GPU per step, random-init weights seed 0", "batch_per_gpu": B, "execution": "cuda-graph replay" if use_graphs else "eager launches", "parallelism": f"dp{world} (independent streams)",
                    "l2": "no explicit flush: each step streams ~2 GB of weights + activations, far larger than the 126 MB L2"},
-        "p50_ms_per_image_e2e": sorted(lat)[len(lat) // 2] * 1e3 / B,
+        "p50_ms_per_image_e2e": _pct(lat, .5) * 1e3 / B, "p90_ms_per_image_e2e": _pct(lat, .9) * 1e3 / B,
         "e2e": {"value": pixels * MP / t_e2e, "unit": "MP/s", "ms_per_step": t_e2e * 1e3,
                 "h2d_bytes_per_step": B * (nsym * 2 + (H // 64) * (W // 64) * 4),
                 "d2h_bytes_per_step": B * (nsym * 2 + 3 * H * W * 4)},
@@ -348,24 +479,35 @@ def run_ours(args):
     }
     if pipe is not None:
         res["e2e_pipelined"] = pipe
-    if not args.no_cpu_baseline and world >= 1:
+    if extras:
+        res["configs"] = extras
+    if not args.no_cpu_baseline and world == 1:
         res["cpu_baseline"] = cpu_baseline(args)
     print(json.dumps(res))
 
 
 def cpu_baseline(args):
-    """The oracle port timed on this box's host cores on a bounded sample of the workload (~10-30 s of CPU work):
-    two decodes of the 768x768 workload itself when they fit, else of a smaller square image."""
-    orc, cores, side, t256 = _oracle_and_size(args, (2, 30.0))
-    stream, _, _ = orc.codec.make_stream(side, side, seed=1234)
-    n = 2 if side > 256 else 8
-    t0 = time.perf_counter()
-    for _ in range(n):
-        orc.decode(stream)
-    dt = (time.perf_counter() - t0) / n
-    return {"value": side * side * MP / dt, "unit": "MP/s", "cores": cores, "kind": "port",
-            "sample": f"{n} x one synthetic {side}x{side} stream, full decode path incl. rANS (MP/s is size-normalised), "
-                      f"fp32 torch CPU, {dt * n:.1f} s"}
+    """The oracle port timed on this box's host cores on a bounded sample (~30 s of CPU work in all): two decodes of the
+    768x768 workload itself on all threads, plus BASELINE.json configs[0] -- one synthetic 256x256 image, fp32 -- p50 on
+    all threads and on ONE thread (the reference's own default, src/inference.py:29 torch.set_num_threads(1))."""
+    import torch
+    orc, cores = _oracle()
+    s768, _, _ = orc.codec.make_stream(768, 768, seed=1234)
+    s256, _, _ = orc.codec.make_stream(256, 256, seed=1234)
+    _time_decodes(orc, s256, 1)                                      # warm-up (thread pools, allocator)
+    t256 = _time_decodes(orc, s256, 3)
+    t768 = _time_decodes(orc, s768, 2)
+    dt = sum(t768) / len(t768)
+    torch.set_num_threads(1)
+    _time_decodes(orc, s256, 1)
+    t256_1 = _time_decodes(orc, s256, 3)
+    torch.set_num_threads(cores)
+    p50 = lambda ts: sorted(ts)[len(ts) // 2]
+    return {"value": 768 * 768 * MP / dt, "unit": "MP/s", "cores": cores, "kind": "port",
+            "sample": f"2 x one synthetic 768x768 stream, full decode path incl. rANS, fp32 torch CPU, {sum(t768):.1f} s",
+            "config0_256x256": {"p50_ms_all_threads": p50(t256) * 1e3, "MPs_all_threads": 256 * 256 * MP / p50(t256),
+                                "p50_ms_one_thread": p50(t256_1) * 1e3, "MPs_one_thread": 256 * 256 * MP / p50(t256_1),
+                                "runs": "1 warm-up + 3 timed each", "threads": cores}}
 
 
 def main():
@@ -376,7 +518,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=768)
     ap.add_argument("--batch", type=int, default=1)
-    ap.add_argument("--ref-size", type=int, default=0, help="side of the CPU sample image; 0 = largest that fits the time budget")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[2..4] entries (kodak64, z_only_768, s2048)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipeline", type=int, default=3, help="images in flight for the extra e2e_pipelined figure (0/1 = skip)")
     ap.add_argument("--workload", default="single768", choices=["single768", "kodak64"],

@@ -126,6 +126,11 @@ typedef struct {
    * CTAs issue cp.async.bulk.prefetch.L2 for disjoint slices of it before starting their own work */
   const void* prefetch_ptr;
   int64_t prefetch_bytes;
+  /* 1 = the launch plan must not depend on the batch size or the SM count: no split-K, no column-copy / transposed
+   * tile, so every output element is accumulated in the same (tap, 64-channel chunk) order whatever n_img is.  Set
+   * for every layer that feeds the entropy parameters (hyper-synthesis, prior nets): encoder and decoder must see
+   * bit-identical scales (compression_model.py:369-407), also when one of them batches. */
+  int32_t deterministic;
 } onedc_igemm_desc;
 
 /* diagnostics: when set (device pointer to 148 x 16 int64, zeroed by the caller) every igemm CTA records clock
@@ -207,7 +212,7 @@ int onedc_build_indexes(const void* scales, int32_t in_dtype, const uint8_t* lut
  * (sym == NULL: means only, the z-only model).  step 0 also zero-fills the inactive positions. */
 int onedc_dequant_accum(const int16_t* sym, const void* means, int64_t means_ld, void* y_hat, int64_t y_ld,
                         int32_t step, int32_t n_img, int32_t h, int32_t w, int32_t c4, void* stream);
-/* encode-side twin: sym[n][c][h][w] = clamp(round_half_even(y - means), +-30000) at active positions and
+/* encode-side twin: sym[n][c][h][w] = clamp(round_half_even(bf16(y - means)), +-30000) at active positions and
  * y_hat as in dequant_accum */
 int onedc_quantize_residual(const void* y, int64_t y_in_ld, const void* means, int64_t means_ld, int16_t* sym,
                             void* y_hat, int64_t y_ld, int32_t step, int32_t n_img, int32_t h, int32_t w,

@@ -2,8 +2,13 @@
 (/root/reference/src/models/sd15_onedc_codec_stage1/codec_module.py:184-454) and the
 `CompressionModel` four-part prior (modules/entropy/compression_model.py:369-465).
 
-Same entry points and return values (`decode(fp=, stream=)`, `_decompress(...)`, `update(force)`,
-attributes `ds`, `cond_ds`, `index_unit_length`, `entropy_coder`, `gaussian_encoder`), same wire format.
+Same constructor arguments, entry points and return values (`IntraNoAR(cond_ch, ctrl_ch, internal_ch, bottleneck_ch,
+unet_ch_config, z_fsq_levels)`, `load_state_dict(sd, strict=True)`, `decode(fp=, stream=)`, `_decompress(...)`,
+`decompress_four_part_prior(common_params, adaptor_1, adaptor_2, adaptor_3, y_spatial_prior, reduction)`,
+`update(force)`, attributes `ds`, `cond_ds`, `index_unit_length`, `entropy_coder`, `gaussian_encoder`, the sub-module
+names `hyper_dec`, `y_prior_fusion`, `y_spatial_prior*`, `semantic_adaptor`, `dec`), same wire format; the z-only
+model's `forward(..., fix_codec=True)` result dict (models/sd15_onedc_codec_z_only/codec_module.py:263-308) from the
+z indices on (the analysis transform that would produce them is out of scope).
 Added, without changing the old calls: `decode_batch(streams)` (same-size images batched through every
 kernel, host rANS of the images on a GIL-free thread pool) and `compress_synthetic(...)`, the encode-side
 twin of the 4-step loop used to produce decodable streams (the analysis transform is out of scope).
@@ -20,6 +25,7 @@ import torch
 from . import bitstream, ops
 from .entropy_models import EntropyCoder, GaussianEncoder, StreamDecoder
 from .nets import HyperSynthesis, LatentSynthesisNet, SemanticAdaptorNet, SpatialPrior
+from .weights import LazyNet, codec_spec
 
 
 class CompressionModel:
@@ -42,18 +48,36 @@ class CompressionModel:
         return self.gaussian_encoder.get_cdf_info()
 
 
-class IntraNoAR(CompressionModel):
-    def __init__(self, state_dict, device="cuda", cond_ch=4, ctrl_ch=320, internal_ch=512, bottleneck_ch=128,
-                 unet_ch_config=(512, 768, 768), z_fsq_levels=(4,) * 7, rans_threads=None):
-        super().__init__(y_distribution="gaussian", z_channel=bottleneck_ch, ec_thread=False, stream_part=1)
-        assert (internal_ch, bottleneck_ch, tuple(unet_ch_config), tuple(z_fsq_levels)) == \
-            (512, 128, (512, 768, 768), (4,) * 7), "only the published OneDC configuration is built"
+class _Seq:
+    """callable chain of kernel-launch blocks (the reference's nn.Sequential attributes)"""
+
+    def __init__(self, mods):
+        self.mods = list(mods)
+
+    def __call__(self, t):
+        for m in self.mods:
+            t = m(t)
+        return t
+
+
+def _nhwc_view(t):
+    """Accepts the internal NHWC tensor or the reference-shaped logical NCHW view of it; returns (NHWC, was_nchw)."""
+    if t.dim() == 4 and t.stride(-1) != 1 and t.stride(1) == 1:
+        return t.permute(0, 2, 3, 1), True
+    return t, False
+
+
+class IntraNoAR(LazyNet, CompressionModel):
+    # analysis-side modules of the reference class (codec_module.py:196-201): present in model_1.safetensors,
+    # not on the decode path
+    IGNORED_PREFIXES = ("enc.", "hyper_enc.", "z_vq.")
+
+    def __init__(self, cond_ch=4, ctrl_ch=320, internal_ch=512, bottleneck_ch=128, unet_ch_config=(512, 768, 768),
+                 z_fsq_levels=(4,) * 7, state_dict=None, device="cuda", rans_threads=None):
+        CompressionModel.__init__(self, y_distribution="gaussian", z_channel=bottleneck_ch, ec_thread=False, stream_part=1)
+        assert (cond_ch, ctrl_ch, internal_ch, bottleneck_ch, tuple(unet_ch_config), tuple(z_fsq_levels)) == \
+            (4, 320, 512, 128, (512, 768, 768), (4,) * 7), "only the published OneDC configuration is built"
         self.device = torch.device(device)
-        sd = state_dict
-        self.hyper = HyperSynthesis(sd, self.device)
-        self.prior = SpatialPrior(sd, self.device)
-        self.semantic_adaptor = SemanticAdaptorNet(sd, self.device)
-        self.dec = LatentSynthesisNet(sd, self.device)
         self.z_fsq_levels = list(z_fsq_levels)
         self.index_unit_length = 14                  # log2(4^7)
         self.ds, self.cond_ds = 64, 8
@@ -61,6 +85,22 @@ class IntraNoAR(CompressionModel):
         self._pool = ThreadPoolExecutor(max_workers=rans_threads or max(1, min(16, (os.cpu_count() or 2) - 1)))
         self._pinned = {}
         self.last_trace = None
+        self._lazy_init(state_dict)
+
+    def _spec(self):
+        return codec_spec()
+
+    def _build(self, sd):
+        self.hyper = HyperSynthesis(sd, self.device)
+        self.prior = SpatialPrior(sd, self.device)
+        self.semantic_adaptor = SemanticAdaptorNet(sd, self.device)
+        self.dec = LatentSynthesisNet(sd, self.device)
+        # the reference's attribute names (codec_module.py:203-217), as callables over NHWC bf16 tensors
+        self.hyper_dec = self.hyper.hyper_dec
+        self.y_prior_fusion = self.hyper.y_prior_fusion
+        self.y_spatial_prior_adaptor_1, self.y_spatial_prior_adaptor_2, self.y_spatial_prior_adaptor_3 = self.prior.adaptors[1:]
+        self.y_spatial_prior = _Seq(self.prior.prior)
+        self.y_spatial_prior_reduction = self.prior.reduce
 
     # ------------------------------------------------------------------------------------------
     def _pin(self, name, shape, dtype):
@@ -85,9 +125,18 @@ class IntraNoAR(CompressionModel):
 
     @torch.no_grad()
     def _decompress(self, bit_stream_y, bit_stream_z, pad_height, pad_width, bit_stream_caption=None, **kwargs):
-        x_hat, y_sem = self._decompress_batch([bit_stream_y], [bit_stream_z], pad_height, pad_width)
-        # logical NCHW like the reference (memory stays NHWC)
-        return x_hat.permute(0, 3, 1, 2), y_sem.permute(0, 3, 1, 2)
+        """codec_module.py:418-454, call for call; tensors are logical NCHW views over NHWC memory like the reference's."""
+        self.entropy_coder.set_stream(bit_stream_y)
+        z_idx = self.parse_z([bit_stream_z], pad_height, pad_width)
+        params, z_semantic = self.hyper_dec(ops.fsq_codes(z_idx))
+        params = self.y_prior_fusion(params)
+        y_hat = self.decompress_four_part_prior(params.permute(0, 3, 1, 2),
+                                                self.y_spatial_prior_adaptor_1, self.y_spatial_prior_adaptor_2,
+                                                self.y_spatial_prior_adaptor_3, self.y_spatial_prior,
+                                                self.y_spatial_prior_reduction)
+        y_semantic = self.semantic_adaptor(z_semantic)
+        x_hat = self.dec(y_hat.permute(0, 2, 3, 1), y_semantic)
+        return x_hat.permute(0, 3, 1, 2), y_semantic.permute(0, 3, 1, 2)
 
     @torch.no_grad()
     def decode_batch(self, streams):
@@ -109,15 +158,34 @@ class IntraNoAR(CompressionModel):
         z_idx = self.parse_z(z_streams, pad_height, pad_width)
         common, z_sem = self.hyper(z_idx)
         decoders = [StreamDecoder(self.entropy_coder, s, self.gaussian_encoder.cdf_group_index) for s in y_streams]
-        y_hat = self.decompress_four_part_prior(common, decoders, trace)
+        y_hat = self._four_part_loop(common, decoders, trace)
         y_sem = self.semantic_adaptor(z_sem)
         x_hat = self.dec(y_hat, y_sem)
         return x_hat, y_sem
 
     # ---- the 4-step loop (compression_model.py:369-407) ------------------------------------------
-    def decompress_four_part_prior(self, common_params, decoders, trace=None):
+    @torch.no_grad()
+    def decompress_four_part_prior(self, common_params, y_spatial_prior_adaptor_1, y_spatial_prior_adaptor_2,
+                                   y_spatial_prior_adaptor_3, y_spatial_prior, y_spatial_prior_reduction=None):
+        """Reference signature (compression_model.py:369-373).  Reads the y stream from `self.entropy_coder`
+        (`set_stream` first, as `_decompress` does); one image, like the reference.  `common_params` may be the
+        internal NHWC tensor or its logical NCHW view; y_hat comes back in the same form."""
+        assert y_spatial_prior_reduction is not None, "the OneDC codec always reduces the common params (codec_module.py:213)"
+        common, nchw = _nhwc_view(common_params)
+        assert common.shape[0] == 1, "one stream per call; batches go through decode_batch"
+        y_hat = self._four_part_loop(common, [self.entropy_coder], None,
+                                     (None, y_spatial_prior_adaptor_1, y_spatial_prior_adaptor_2, y_spatial_prior_adaptor_3),
+                                     y_spatial_prior, y_spatial_prior_reduction)
+        return y_hat.permute(0, 3, 1, 2) if nchw else y_hat
+
+    def _four_part_loop(self, common_params, decoders, trace=None, adaptors=None, prior=None, reduction=None):
+        """decoders: one rANS cursor per image (objects with `decode_into(idx_ptr, n, out_ptr)`)."""
+        adaptors = adaptors or self.prior.adaptors
+        prior = prior or self.y_spatial_prior
+        reduction = reduction or self.y_spatial_prior_reduction
         n, h, w, _ = common_params.shape
-        params = self.prior.init_params(common_params)           # [..., :128] = y_hat_so_far, [..., 128:] = reduced
+        params = torch.empty((n, h, w, 256), device=self.device, dtype=torch.bfloat16)
+        reduction(common_params, out=params[..., 128:])          # [..., :128] = y_hat_so_far, [..., 128:] = reduced
         y_hat = params[..., :128]
         nsym = 32 * h * w
         idx_dev = torch.empty((n, 32, h, w), device=self.device, dtype=torch.int16)
@@ -129,7 +197,7 @@ class IntraNoAR(CompressionModel):
         stream = torch.cuda.current_stream()
         for k in range(4):
             if k > 0:
-                sm = self.prior.step(k, params)
+                sm = prior(adaptors[k](params))
             ops.scale_to_index(sm[..., :128], lut, k, idx_dev)
             idx_host.copy_(idx_dev.view(n, nsym), non_blocking=True)
             stream.synchronize()
@@ -169,15 +237,52 @@ class IntraNoAR(CompressionModel):
     def decode_z_only(self, z_idx):
         """z_idx int32 [B,hz,wz] on the device -> (x_hat, y_sem) NHWC."""
         common, z_sem = self.hyper(z_idx)
-        params = self.prior.init_params(common)
+        y_hat = self.forward_four_part_prior_recon_with_z(None, common)
+        y_sem = self.semantic_adaptor(z_sem)
+        return self.dec(y_hat, y_sem), y_sem
+
+    @torch.no_grad()
+    def forward(self, x=None, cond=None, fix_encoder=False, fix_codec=False, z_vq_indices=None):
+        """Decoder half of the z-only model's `forward(x, cond, fix_codec=True)`
+        (models/sd15_onedc_codec_z_only/codec_module.py:231-308): same result-dict keys.  The analysis transform
+        (`enc`, `hyper_enc`, FSQ forward) is out of scope, so the z indices it would produce are passed in as
+        `z_vq_indices` (int [B,hz,wz]); with y_q = 0 and scales_hat = 0 the reference's bit terms are exactly 0
+        (probs_to_bits of probability 1, LowerBound 0)."""
+        assert z_vq_indices is not None, "onedc_b200 has no analysis transform: pass z_vq_indices (SURVEY.md section 6)"
+        z_idx = z_vq_indices.to(self.device, dtype=torch.int32)
+        params, z_semantic = self.hyper_dec(ops.fsq_codes(z_idx))
+        params = self.y_prior_fusion(params)
+        y_hat = self.forward_four_part_prior_recon_with_z(None, params)
+        y_semantic = self.semantic_adaptor(z_semantic)
+        x_hat = self.dec(y_hat, y_semantic)
+        zero = torch.zeros((), device=self.device)
+        nchw = lambda t: t.permute(0, 3, 1, 2)
+        return {"x_hat": nchw(x_hat), "y_hat": nchw(y_hat), "bit": zero, "bpp": zero, "bpp_y": zero, "bpp_hard_y": zero,
+                "y_semantic": nchw(y_semantic), "z_semantic": nchw(z_semantic), "z_vq_indices": z_vq_indices,
+                "params_hat": nchw(params), "y_orig": None}
+
+    __call__ = forward
+
+    @torch.no_grad()
+    def forward_four_part_prior_recon_with_z(self, y, common_params, y_spatial_prior_adaptor_1=None,
+                                             y_spatial_prior_adaptor_2=None, y_spatial_prior_adaptor_3=None,
+                                             y_spatial_prior=None, y_spatial_prior_reduction=None, write=False):
+        """compression_model.py:421-465: y_hat_k = means_k * mask_k (`y` only lends its shape there; unused here)."""
+        common, nchw = _nhwc_view(common_params)
+        adaptors = (None, y_spatial_prior_adaptor_1 or self.y_spatial_prior_adaptor_1,
+                    y_spatial_prior_adaptor_2 or self.y_spatial_prior_adaptor_2,
+                    y_spatial_prior_adaptor_3 or self.y_spatial_prior_adaptor_3)
+        prior = y_spatial_prior or self.y_spatial_prior
+        n, h, w, _ = common.shape
+        params = torch.empty((n, h, w, 256), device=self.device, dtype=torch.bfloat16)
+        (y_spatial_prior_reduction or self.y_spatial_prior_reduction)(common, out=params[..., 128:])
         y_hat = params[..., :128]
         sm = common
         for k in range(4):
             if k > 0:
-                sm = self.prior.step(k, params)
+                sm = prior(adaptors[k](params))
             ops.dequant_accum(None, sm[..., 128:], y_hat, k)
-        y_sem = self.semantic_adaptor(z_sem)
-        return self.dec(y_hat, y_sem), y_sem
+        return y_hat.permute(0, 3, 1, 2) if nchw else y_hat
 
     # ---- encode-side twin of the loop (compression_model.py:303-358) ---------------------------------
     @torch.no_grad()

@@ -165,8 +165,12 @@ __global__ void __launch_bounds__(128) dequant_kernel(int16_t* sym, const __nv_b
       for (int j = 0; j < 4; j++) {
         float q0, q1;
         if (MODE == 1) {
-          q0 = fminf(fmaxf(rintf(bf16lo(yw[j]) - bf16lo(mw[j])), -30000.f), 30000.f);
-          q1 = fminf(fmaxf(rintf(bf16hi(yw[j]) - bf16hi(mw[j])), -30000.f), 30000.f);
+          // process_with_mask (compression_model.py:224-239) under bf16 autocast: the residual y - means is a bf16
+          // tensor BEFORE torch.round (round half to even) sees it
+          const float r0 = __bfloat162float(__float2bfloat16(bf16lo(yw[j]) - bf16lo(mw[j])));
+          const float r1 = __bfloat162float(__float2bfloat16(bf16hi(yw[j]) - bf16hi(mw[j])));
+          q0 = fminf(fmaxf(rintf(r0), -30000.f), 30000.f);
+          q1 = fminf(fmaxf(rintf(r1), -30000.f), 30000.f);
           tile[v * 8 + 2 * j][pl] = (int16_t)q0;
           tile[v * 8 + 2 * j + 1][pl] = (int16_t)q1;
         } else if (sym != nullptr) {

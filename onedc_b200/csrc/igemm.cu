@@ -1238,7 +1238,7 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
     const int mt = d->n_img * ((Ho + th0 - 1) / th0) * ((Wo + tw0 - 1) / tw0);
     const int taps0 = d->ntaps > 0 ? d->ntaps : d->ksize * d->ksize;
     const int kit = taps0 * ((d->a_c[0] + 63) / 64 + (d->a_c[1] + 63) / 64);
-    const bool will_split = d->splitk_ws != nullptr && mt * p.n_tiles * 2 <= sm_count() && kit >= 32 &&
+    const bool will_split = !d->deterministic && d->splitk_ws != nullptr && mt * p.n_tiles * 2 <= sm_count() && kit >= 32 &&
                             sm_count() / (mt * p.n_tiles) >= 4;
     while (!will_split && p.BN % 64 == 0 && p.BN >= 128 && d->cout % (p.BN / 2) == 0 &&
            mt * ((d->cout + p.BN / 2 - 1) / (p.BN / 2)) <= sm_count()) {
@@ -1332,7 +1332,7 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
     const int octile = pair ? p.BN / 2 : p.BN;
     const bool fast_all = p.vec_ok && (d->cout % p.BN == 0) && (octile % 32 == 0) &&
                           (d->store_mode == ST_NORMAL || d->store_mode == ST_QUAD || (d->store_mode == ST_PIXSHUF && d->ps_c % 32 == 0));
-    if (d->impl != 1 && p.ws != nullptr && p.counters != nullptr && fast_all && tiles * 2 <= sm_count() &&
+    if (d->impl != 1 && !d->deterministic && p.ws != nullptr && p.counters != nullptr && fast_all && tiles * 2 <= sm_count() &&
         kiters >= 16 && tiles <= d->splitk_max_tiles / 2) {
       int s = sm_count() / tiles;
       if (s > kiters / 8) s = kiters / 8;
@@ -1346,7 +1346,7 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
   p.colmode = 0;
   {
     static const bool colmode_on = getenv("ONEDC_COLMODE") == nullptr || getenv("ONEDC_COLMODE")[0] != '0';
-    if (colmode_on && d->impl != 1 && p.splits == 1 && d->stride == 1 && p.taps > 1 && !d->w_batched) {
+    if (colmode_on && d->impl != 1 && !d->deterministic && p.splits == 1 && d->stride == 1 && p.taps > 1 && !d->w_batched) {
       int miny = 99, maxy = -99, ng = 0;
       bool ok = true;
       memset(p.cm_nt, 0, sizeof(p.cm_nt));

@@ -99,6 +99,11 @@ class EntropyCoder:
                                                     out.ctypes.data), "rans decode")
         return out
 
+    def decode_into(self, idx_ptr, n, out_ptr, cdf_group_index=0):
+        """Raw-pointer form on the coder's own cursor (pinned host buffers of the 4-step loop); GIL released."""
+        L.check(self._lib.onedc_rans_decoder_decode(self._dec, self.tables(cdf_group_index), idx_ptr, n, out_ptr),
+                "rans decode")
+
     def decode_stream(self, indexes, cdf_group_index):
         rv = self.decode_stream_np(indexes.detach().to(torch.int16).cpu().numpy(), cdf_group_index)
         return torch.from_numpy(rv.astype(np.float32))

@@ -169,6 +169,42 @@ class GraphedDecoder:
             self.launches_res = lib.launch_count() - n0      # kernels of this library inside one replay
         torch.cuda.synchronize()
 
+    def capture_z_only(self):
+        """z-only model: indices -> image is one graph (no y stream, no host round trip), D2H of the image included."""
+        if getattr(self, "g_z", None) is not None:
+            return
+        from . import lib
+        assert self.lane_base == 0
+        with torch.no_grad():
+            x_hat, y_sem = self.codec.decode_z_only(self.z_dev)          # eager warm-up
+            self.model.generate(x_hat, y_sem)
+            torch.cuda.synchronize()
+            n0 = lib.launch_count()
+            self.g_z = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_z):
+                x_hat, y_sem = self.codec.decode_z_only(self.z_dev)
+                self.img_z = self.model.generate(x_hat, y_sem)
+                self.img_host.copy_(self.img_z, non_blocking=True)
+            self.launches_z = lib.launch_count() - n0
+        torch.cuda.synchronize()
+
+    def run_z_only(self):
+        self.capture_z_only()
+        self.g_z.replay()
+        return self.img_z
+
+    def decode_z_only(self, z_idx):
+        """z_idx int [B,hz,wz] (host or device) -> fresh device image; the pinned host copy is in `img_host`."""
+        self.capture_z_only()
+        if z_idx.is_cuda:
+            self.z_dev.copy_(z_idx.to(torch.int32), non_blocking=True)
+        else:
+            self.z_host.copy_(z_idx.to(torch.int32))
+            self.z_dev.copy_(self.z_host, non_blocking=True)
+        self.g_z.replay()
+        torch.cuda.current_stream().synchronize()
+        return self.img_z.clone()
+
     # ---------------------------------------------------------------------------------------------
     def decode(self, streams):
         """streams: B reference-format containers of this padded size -> pinned host images [B,3,H,W] fp32
@@ -206,6 +242,15 @@ class GraphedDecoder:
         self.last_rans_ms = t_rans * 1e3
         return self.img_host, hdrs
 
+    def release(self):
+        """Drops the captured graphs, their private memory pools and the pinned buffers (LRU eviction, weight reload)."""
+        torch.cuda.synchronize(self.dev)
+        self.graphs = self.g_res = self.g_z = self.img_dev = self.img_res = self.img_z = None
+        for name in ("common", "z_sem", "params", "sm", "y_sem", "cat", "ctx_kv", "z_host", "z_dev", "idx_host", "sym_host",
+                     "idx_dev", "sym_dev", "img_host", "syms_res"):
+            self.__dict__.pop(name, None)
+        self._keep = []
+
     def set_resident_inputs(self, z_idx, syms):
         self.z_dev.copy_(z_idx)
         for a, b in zip(self.syms_res, syms):
@@ -234,6 +279,11 @@ class PipelinedDecoder:
             with torch.cuda.stream(st):
                 sl.capture()
         torch.cuda.synchronize()
+
+    def release(self):
+        for sl in self.slots:
+            sl.release()
+        self.slots = []
 
     def decode_many(self, streams, out=None):
         """streams: reference-format containers of this padded size -> list of fp32 [1,3,H,W] host tensors (cropped),

@@ -12,42 +12,93 @@ libonedc_b200 kernels.  Extra entry points (the old ones unchanged): `decode_bat
 `decode_z_only(z_idx)` for the hyperprior-only (0.0034 bpp) model of models/sd15_onedc_codec_z_only.
 """
 import math
+import os
+from collections import OrderedDict
 
 import torch
 
 from . import ops
 from .codec_module import IntraNoAR
 from .nets import UNet, VAEDecoder, alphas_cumprod_sd15
+from .weights import load_checkpoint_file, vae_decoder_state_dict
 
 VAE_SCALING = 0.18215
 
 
+def _arg(args, name, default):
+    """args is the reference's OmegaConf/argparse namespace (or a dict, or None)"""
+    if args is None:
+        return default
+    if isinstance(args, dict):
+        v = args.get(name, default)
+    else:
+        v = getattr(args, name, default)
+    return default if v is None else v
+
+
 class SD15_1step_codec_stage1:
-    def __init__(self, args=None, accelerator=None, state_dicts=None, device="cuda", vae_attn_patch=16,
-                 conditioning_timestep=999):
-        assert state_dicts is not None, "pass (unet_sd, codec_sd, vae_sd) reference-named state dicts"
+    """Constructed like the reference, `SD15_1step_codec_stage1(args, accelerator)` (model...py:18; the fields read are
+    `args.vae_attn_patch`, `args.conditioning_timestep`, `args.codec.*`, `accelerator.device`), without weights; then
+    `model.feedforward_model.load_state_dict(sd, strict=True)` / `model.codec_model.load_state_dict(sd, strict=True)`
+    exactly as src/inference.py:87-93 does.  The reference pulls the SD-2.1 VAE from the HF hub inside __init__
+    (model...py:43-45); there is no network here, so the VAE decoder is loaded from `args.vae_large_path` / the
+    ONEDC_VAE_PATH environment variable (a diffusers `vae/diffusion_pytorch_model.safetensors`) or through
+    `model.vae_large.load_state_dict(...)`.  A network that is never loaded runs on its seed-0 random initialisation
+    (what every test and bench here uses: no checkpoints exist offline).  `state_dicts=(unet, codec, vae)` is the
+    shortcut the tests use."""
+
+    def __init__(self, args=None, accelerator=None, state_dicts=None, device=None, vae_attn_patch=None,
+                 conditioning_timestep=None):
         if not torch.cuda.is_available():
             raise RuntimeError("onedc_b200 needs a CUDA device (sm_100a); there is no CPU path")
-        unet_sd, codec_sd, vae_sd = state_dicts
+        unet_sd, codec_sd, vae_sd = state_dicts if state_dicts is not None else (None, None, None)
         self.args, self.accelerator = args, accelerator
+        if device is None:
+            device = getattr(accelerator, "device", None) or "cuda"
         self.device = torch.device(device)
-        self.conditioning_timestep = conditioning_timestep
-        self.vae_attn_patch = vae_attn_patch
-        self.codec_model = IntraNoAR(codec_sd, self.device)
-        self.feedforward_model = UNet(unet_sd, self.device, conditioning_timestep)
-        self.vae_large = VAEDecoder(vae_sd, self.device, vae_attn_patch)
-        a = alphas_cumprod_sd15().double()[conditioning_timestep]
+        if self.device.type != "cuda":
+            raise RuntimeError("onedc_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.conditioning_timestep = int(conditioning_timestep if conditioning_timestep is not None
+                                         else _arg(args, "conditioning_timestep", 999))
+        self.vae_attn_patch = int(vae_attn_patch if vae_attn_patch is not None else _arg(args, "vae_attn_patch", 16))
+        self.use_large_vae = True
+        codec_args = _arg(args, "codec", None)
+        self.codec_model = IntraNoAR(cond_ch=4, ctrl_ch=320,
+                                     internal_ch=_arg(codec_args, "internal_ch", 512),
+                                     bottleneck_ch=_arg(codec_args, "bottleneck_ch", 128),
+                                     unet_ch_config=tuple(_arg(codec_args, "unet_ch_config", (512, 768, 768))),
+                                     z_fsq_levels=tuple(_arg(codec_args, "z_fsq_levels", (4,) * 7)),
+                                     state_dict=codec_sd, device=self.device)
+        self.feedforward_model = UNet(unet_sd, self.device, self.conditioning_timestep)
+        vae_path = _arg(args, "vae_large_path", None) or os.environ.get("ONEDC_VAE_PATH")
+        if vae_sd is None and vae_path:
+            vae_sd = vae_decoder_state_dict(load_checkpoint_file(vae_path))
+        self.vae_large = VAEDecoder(vae_sd, self.device, self.vae_attn_patch)
+        a = alphas_cumprod_sd15().double()[self.conditioning_timestep]
         self.sqrt_alpha = float(a.sqrt())
         self.sqrt_1m_alpha = float((1 - a).sqrt())
         self.last_stages = None
         # CUDA-graph replay of the fixed per-size launch sequence (onedc_b200/graphs.py); eager when tracing stages
         self.use_graphs = True
-        self._graphed = {}
+        self._graphed = OrderedDict()
+        self.max_cached_sizes = int(os.environ.get("ONEDC_GRAPH_CACHE", "4"))
+        for net in (self.codec_model, self.feedforward_model, self.vae_large):
+            net._on_load.append(self._weights_changed)          # captured graphs hold the old weight pointers
+
+    def release_graphs(self):
+        """Drops every cached per-size decoder (captured graphs, their memory pools, pinned buffers)."""
+        while self._graphed:
+            self._graphed.popitem()[1].release()
+
+    _weights_changed = release_graphs
 
     def eval(self):
         return self
 
     def prepare(self):
+        return self
+
+    def load_part_ckpt(self):
         return self
 
     # ------------------------------------------------------------------------------------------
@@ -66,12 +117,23 @@ class SD15_1step_codec_stage1:
                           y_sem=y_sem.float().permute(0, 3, 1, 2).cpu())
         return img
 
+    def _cache_get(self, key, make):
+        """LRU over (batch, padded size[, depth]): every entry owns two private CUDA-graph memory pools holding all
+        activations of one decode (~1.1 GB at 768x768, ~8 GB at 2048x2048, batch 1) plus pinned host buffers, and a
+        new size costs a warm-up pass + capture (~1 s), so mixed-size datasets keep at most `max_cached_sizes`
+        (ONEDC_GRAPH_CACHE, default 4) entries; the evicted decoder's graphs and pools are released."""
+        if key in self._graphed:
+            self._graphed.move_to_end(key)
+            return self._graphed[key]
+        while len(self._graphed) >= max(1, self.max_cached_sizes):
+            _, old = self._graphed.popitem(last=False)
+            old.release()
+        self._graphed[key] = make()
+        return self._graphed[key]
+
     def graphed(self, batch, pad_h, pad_w):
         from .graphs import GraphedDecoder
-        key = (batch, pad_h, pad_w)
-        if key not in self._graphed:
-            self._graphed[key] = GraphedDecoder(self, batch, pad_h, pad_w)
-        return self._graphed[key]
+        return self._cache_get((batch, pad_h, pad_w), lambda: GraphedDecoder(self, batch, pad_h, pad_w))
 
     @torch.no_grad()
     def decode(self, fp=None, stream=None, stages=None):
@@ -103,10 +165,7 @@ class SD15_1step_codec_stage1:
     def pipelined(self, pad_h, pad_w, depth=2):
         """Decoder that keeps `depth` images of this padded size in flight on the GPU (graphs.PipelinedDecoder)."""
         from .graphs import PipelinedDecoder
-        key = ("pipe", pad_h, pad_w, depth)
-        if key not in self._graphed:
-            self._graphed[key] = PipelinedDecoder(self, pad_h, pad_w, depth)
-        return self._graphed[key]
+        return self._cache_get(("pipe", pad_h, pad_w, depth), lambda: PipelinedDecoder(self, pad_h, pad_w, depth))
 
     @torch.no_grad()
     def decode_many(self, streams, depth=2):
@@ -123,5 +182,10 @@ class SD15_1step_codec_stage1:
 
     @torch.no_grad()
     def decode_z_only(self, z_idx, stages=None):
+        """Hyperprior-only model (models/sd15_onedc_codec_z_only): int [B,hz,wz] z indices (host or device) -> padded
+        fp32 image [B,3,64hz,64wz].  One CUDA-graph replay per call unless `stages` asks for the eager trace."""
+        if stages is None and self.use_graphs:
+            b, hz, wz = z_idx.shape
+            return self.graphed(b, hz * 64, wz * 64).decode_z_only(z_idx)
         x_hat, y_sem = self.codec_model.decode_z_only(z_idx.to(self.device, dtype=torch.int32))
         return self.generate(x_hat, y_sem, stages)

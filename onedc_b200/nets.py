@@ -19,7 +19,7 @@ from . import ops
 from .ops import (ACT_LRELU, ACT_NONE, ConvW, DepthwiseW, GroupNorm, LayerNorm, TapConv3x3, UpConv, igemm, pair_permute,
                   pixshuf_permute)
 from .lib import EPI_GEGLU, EPI_PAIR_LRELU, ST_PIXSHUF, ST_TRANSPOSED
-from .weights import merge_lora
+from .weights import LazyNet, merge_lora, unet_spec, vae_spec
 
 
 def _wb(sd, name):
@@ -33,9 +33,10 @@ class DCB4:
     """DepthConvBlock4 = DepthConv (1x1+LReLU, dw3x3, 1x1 [+1x1 adaptor]) + ConvFFN3.
     5 launches: igemm, dwconv, igemm (adaptor folded in as a second K source), igemm (pair epilogue), igemm."""
 
-    def __init__(self, sd, p, cin, cout, dev, out_stats=False):
+    def __init__(self, sd, p, cin, cout, dev, out_stats=False, det=False):
         self.cin, self.cout = cin, cout
         self.out_stats = out_stats            # output feeds a GroupNorm: fuse its statistics into the last epilogue
+        self.det = det                        # entropy path: batch-independent launch plan (bit-identical scales)
         w, b = _wb(sd, p + ".block.0.conv1.0")
         self.conv1 = ConvW(w, b, dev)
         self.dw = DepthwiseW(sd[p + ".block.0.depth_conv.weight"].float(), sd[p + ".block.0.depth_conv.bias"].float(), dev)
@@ -49,30 +50,32 @@ class DCB4:
         self.ffn_out = ConvW(*_wb(sd, p + ".block.1.conv_out"), dev)
 
     def __call__(self, x, out=None):
-        t = igemm(x, self.conv1, act=ACT_LRELU, slope=0.01)
+        det = self.det
+        t = igemm(x, self.conv1, act=ACT_LRELU, slope=0.01, det=det)
         t = ops.dwconv3x3(t, self.dw)
         if self.cin != self.cout:
-            h = igemm(t, self.conv2, x2=x)
+            h = igemm(t, self.conv2, x2=x, det=det)
         else:
-            h = igemm(t, self.conv2, res=x)
-        f = igemm(h, self.ffn_in)
-        return igemm(f, self.ffn_out, res=h, out=out, stats=self.out_stats)
+            h = igemm(t, self.conv2, res=x, det=det)
+        f = igemm(h, self.ffn_in, det=det)
+        return igemm(f, self.ffn_out, res=h, out=out, stats=self.out_stats, det=det)
 
 
 class RBU:
     """ResidualBlockUpsample: two 1x1 -> PixelShuffle(2) branches (shuffle fused into the store), LReLU,
     3x3 conv + LReLU(0.1) + identity."""
 
-    def __init__(self, sd, p, cin, cout, dev):
-        self.cout = cout
+    def __init__(self, sd, p, cin, cout, dev, det=False):
+        self.cout, self.det = cout, det
         self.subpel = ConvW(*pixshuf_permute(*_wb(sd, p + ".subpel_conv.0")), dev)
         self.up = ConvW(*pixshuf_permute(*_wb(sd, p + ".upsample.0")), dev)
         self.conv = ConvW(*_wb(sd, p + ".conv"), dev)
 
     def __call__(self, x, out=None):
-        a = igemm(x, self.subpel, act=ACT_LRELU, slope=0.01, store=ST_PIXSHUF, ps_c=self.cout)
-        idt = igemm(x, self.up, store=ST_PIXSHUF, ps_c=self.cout)
-        return igemm(a, self.conv, act=ACT_LRELU, slope=0.1, res=idt, out=out)
+        det = self.det
+        a = igemm(x, self.subpel, act=ACT_LRELU, slope=0.01, store=ST_PIXSHUF, ps_c=self.cout, det=det)
+        idt = igemm(x, self.up, store=ST_PIXSHUF, ps_c=self.cout, det=det)
+        return igemm(a, self.conv, act=ACT_LRELU, slope=0.1, res=idt, out=out, det=det)
 
 
 class VQRes:
@@ -121,17 +124,28 @@ class HyperSynthesis:
     def __init__(self, sd, dev):
         self.feat_in = ConvW(*_wb(sd, "hyper_dec.feat_in.0"), dev)
         p = "hyper_dec.to_entropy."
-        self.seq = [DCB4(sd, p + "0", 128, 128, dev), RBU(sd, p + "1", 128, 128, dev), DCB4(sd, p + "2", 128, 128, dev),
-                    RBU(sd, p + "3", 128, 128, dev), DCB4(sd, p + "4", 128, 128, dev),
-                    DCB4(sd, "y_prior_fusion.0", 128, 256, dev), DCB4(sd, "y_prior_fusion.1", 256, 256, dev)]
+        # det=True everywhere: these layers produce the entropy parameters (scales | means)
+        self.seq = [DCB4(sd, p + "0", 128, 128, dev, det=True), RBU(sd, p + "1", 128, 128, dev, det=True),
+                    DCB4(sd, p + "2", 128, 128, dev, det=True), RBU(sd, p + "3", 128, 128, dev, det=True),
+                    DCB4(sd, p + "4", 128, 128, dev, det=True),
+                    DCB4(sd, "y_prior_fusion.0", 128, 256, dev, det=True), DCB4(sd, "y_prior_fusion.1", 256, 256, dev, det=True)]
 
-    def __call__(self, z_idx):
-        codes = ops.fsq_codes(z_idx)
-        z_sem = igemm(codes, self.feat_in, act=ACT_LRELU, slope=0.01)
+    def hyper_dec(self, codes):
+        """HyperDecoder.forward (codec_module.py:162-166): FSQ codes [N,hz,wz,8] -> (z_entropy, z_semantic)"""
+        z_sem = igemm(codes, self.feat_in, act=ACT_LRELU, slope=0.01, det=True)
         t = z_sem
-        for m in self.seq:
+        for m in self.seq[:5]:
             t = m(t)
         return t, z_sem
+
+    def y_prior_fusion(self, t):
+        for m in self.seq[5:]:
+            t = m(t)
+        return t
+
+    def __call__(self, z_idx):
+        t, z_sem = self.hyper_dec(ops.fsq_codes(z_idx))
+        return self.y_prior_fusion(t), z_sem
 
 
 class SpatialPrior:
@@ -141,13 +155,17 @@ class SpatialPrior:
 
     def __init__(self, sd, dev):
         self.reduction = ConvW(*_wb(sd, "y_spatial_prior_reduction"), dev)
-        self.adaptors = [None] + [DCB4(sd, f"y_spatial_prior_adaptor_{i}", 256, 256, dev) for i in (1, 2, 3)]
-        self.prior = [DCB4(sd, f"y_spatial_prior.{i}", 256, 256, dev) for i in range(3)]
+        self.adaptors = [None] + [DCB4(sd, f"y_spatial_prior_adaptor_{i}", 256, 256, dev, det=True) for i in (1, 2, 3)]
+        self.prior = [DCB4(sd, f"y_spatial_prior.{i}", 256, 256, dev, det=True) for i in range(3)]
+
+    def reduce(self, common, out=None):
+        """y_spatial_prior_reduction (1x1 conv 256 -> 128)"""
+        return igemm(common, self.reduction, out=out, det=True)
 
     def init_params(self, common):
         n, h, w, _ = common.shape
         params = torch.empty((n, h, w, 256), device=common.device, dtype=torch.bfloat16)
-        igemm(common, self.reduction, out=params[..., 128:])
+        self.reduce(common, out=params[..., 128:])
         return params
 
     def step(self, k, params):
@@ -309,12 +327,21 @@ class UNetTransformer:
         return igemm(t.view(b, h, w, c), self.proj_out, res=x, stats=True)
 
 
-class UNet:
-    """One-step SD1.5 UNet at a fixed timestep: (x_hat, ctx tokens) -> (eps fp32, reduced fp32), NHWC, 4 ch."""
+class UNet(LazyNet):
+    """One-step SD1.5 UNet at a fixed timestep: (x_hat, ctx tokens) -> (eps fp32, reduced fp32), NHWC, 4 ch.
+    `load_state_dict` takes the reference's `model.safetensors` keys (peft-wrapped diffusers UNet, weights.unet_spec)."""
 
     CH = (320, 640, 1280, 1280)
 
-    def __init__(self, sd, dev, timestep=999):
+    def __init__(self, sd=None, dev="cuda", timestep=999):
+        self.dev, self.timestep = torch.device(dev), timestep
+        self._lazy_init(sd)
+
+    def _spec(self):
+        return unet_spec()
+
+    def _build(self, sd):
+        dev, timestep = self.dev, self.timestep
         f = lambda n: sd[n].float()
         temb = sinusoidal_timestep(timestep)
         emb = torch.nn.functional.silu(temb @ f("time_embedding.linear_1.weight").t() + f("time_embedding.linear_1.bias"))
@@ -357,6 +384,7 @@ class UNet:
 
     def transformers(self):
         """the 16 transformer blocks in call order"""
+        self._ensure()
         out = []
         for blk in self.down:
             out += blk.get("attn", [])
@@ -370,6 +398,7 @@ class UNet:
         return [t.project_ctx(ctx) for t in self.transformers()]
 
     def __call__(self, x, ctx, kvs=None):
+        self._ensure()
         f32 = torch.float32
         kvs = iter(kvs) if kvs is not None else None
         nkv = lambda: next(kvs) if kvs is not None else None
@@ -464,10 +493,28 @@ class VAEWindowAttention:
         return ops.window_merge(o, x, win)                                 # + residual
 
 
-class VAEDecoder:
-    """post_quant_conv is applied in fp32 by x0_prepare; input here is its [hi|lo] bf16 split (8 channels)."""
+class VAEDecoder(LazyNet):
+    """post_quant_conv is applied in fp32 by x0_prepare; input here is its [hi|lo] bf16 split (8 channels).
+    `load_state_dict` takes the decoder half of the SD-2.1 VAE in diffusers naming (weights.vae_spec)."""
 
-    def __init__(self, sd, dev, attn_patch=16):
+    IGNORED_PREFIXES = ("encoder.", "quant_conv.")
+
+    def __init__(self, sd=None, dev="cuda", attn_patch=16):
+        self.dev, self.attn_patch = torch.device(dev), attn_patch
+        self._lazy_init(sd)
+
+    def _spec(self):
+        return vae_spec()
+
+    def set_attn_patch(self, attn_patch):
+        """autoencoders_patch_attn.py:77-81"""
+        assert attn_patch > 0, "attn_patch must be greater than 0"
+        self.attn_patch = attn_patch
+        if self.__dict__["_built"]:
+            self.attn.win = attn_patch
+
+    def _build(self, sd):
+        dev, attn_patch = self.dev, self.attn_patch
         d = "decoder"
         w, b = _wb(sd, d + ".conv_in")
         self.conv_in = ConvW(torch.cat([w, w], dim=1), b, dev)             # W.(hi + lo)
@@ -489,6 +536,7 @@ class VAEDecoder:
         self.pq_b = sd["post_quant_conv.bias"].float()
 
     def __call__(self, z_hilo):
+        self._ensure()
         n, h, w, _ = z_hilo.shape
         t = igemm(z_hilo, self.conv_in, stats=True)
         t = self.mid0(t)

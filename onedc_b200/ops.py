@@ -11,7 +11,8 @@ from . import lib as L
 from .lib import (ACT_GELU, ACT_LRELU, ACT_NONE, ACT_SILU, BF16, EPI_GEGLU, EPI_PAIR_LRELU, EPI_PLAIN, F32,
                   ST_NORMAL, ST_PIXSHUF, ST_QUAD, ST_TRANSPOSED)
 
-# 0 = tcgen05 kernels (product).  1 = SIMT checking kernels; tests flip this to cross-check on the GPU.
+# 0 = tcgen05 kernels (product).  1 = SIMT checking kernels; tests flip this to cross-check on the GPU.  2 = planning
+# only (onedc_igemm takes every decision and launches nothing; bench.py uses it to time a step without its GEMMs).
 IMPL = int(os.environ.get("ONEDC_IMPL", "0"))
 # attention route: "flash" = onedc_attention; "unfused" = batched GEMM + softmax + GEMM (tests only)
 ATTN = os.environ.get("ONEDC_ATTN", "flash")
@@ -25,9 +26,6 @@ PROFILE_INFO = None
 WEIGHT_TRACE = None
 WEIGHT_PLAY = None
 WEIGHT_PREFETCH = os.environ.get("ONEDC_WEIGHT_PREFETCH", "1") == "1"
-# bench-only: names of ops whose launches are skipped (outputs left uninitialised) so that the time of one kernel
-# family inside the graph-replayed step can be measured as a difference of two replays
-SKIP = set()
 
 
 def _prof_begin():
@@ -208,8 +206,9 @@ def _splitk_buffers(device):
 
 
 def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None, out_dtype=torch.bfloat16,
-          store=ST_NORMAL, ps_c=0, w_batched=False, impl=None, quad=0, stats=False):
-    """out = epilogue(conv(x [cat x2], wt)).  `out` may be a channel-slice view of a wider buffer."""
+          store=ST_NORMAL, ps_c=0, w_batched=False, impl=None, quad=0, stats=False, det=False):
+    """out = epilogue(conv(x [cat x2], wt)).  `out` may be a channel-slice view of a wider buffer.
+    det: launch plan independent of batch size / SM count (layers that feed the entropy parameters)."""
     lib = L.load()
     d = L.IgemmDesc()
     p0, n, h, w, c0, s0 = _nhwc(x)
@@ -261,6 +260,7 @@ def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None
         pr, _, _, _, cr, sr = _nhwc(res)
         d.res, d.res_dtype, d.res_ld = pr, _dt(res), sr
     d.impl = IMPL if impl is None else impl
+    d.deterministic = 1 if det else 0
     if SPLITK:
         ws, cnt = _splitk_buffers(x.device)
         d.splitk_ws, d.splitk_ws_floats, d.splitk_counters, d.splitk_max_tiles = ws.data_ptr(), ws.numel(), cnt.data_ptr(), cnt.numel()
@@ -279,8 +279,6 @@ def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None
         abytes = 2.0 * n * h * w * (c0 + c1) + 2.0 * d.cout * d.ktot * taps_ + out.element_size() * float(n * ho * wo * ncols) \
             + (res.element_size() * float(res.numel()) if res is not None else 0.0)
         PROFILE.append(("igemm_bytes", None, None, abytes))
-    if "igemm" in SKIP:
-        d.impl = 2                                   # dry run: same decisions (tiling, split-K, fused statistics), no launch
     wrange = (wt.w.data_ptr(), wt.w.numel() * 2) if isinstance(wt, ConvW) else (0, 0)
     if WEIGHT_TRACE is not None:
         WEIGHT_TRACE.append(wrange)
@@ -307,6 +305,7 @@ def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None
 
 
 _attn_scratch = {}
+_attn_retired = []
 
 
 def _attn_ws(device, floats):
@@ -315,6 +314,8 @@ def _attn_ws(device, floats):
     key = (str(device), SCRATCH_LANE)
     buf = _attn_scratch.get(key)
     if buf is None or buf.numel() < floats:
+        if buf is not None:
+            _attn_retired.append(buf)          # graphs captured earlier have this pointer baked in: never free it
         buf = _attn_scratch[key] = torch.empty(int(floats), device=device, dtype=torch.float32)
     return buf
 
@@ -329,8 +330,6 @@ def attention(q, k, v, out, heads, head_dim, scale=None, impl=None):
     assert b == 1 or (q.stride(0) == sq * q.stride(1) and k.stride(0) == skv * k.stride(1)
                       and v.stride(0) == skv * v.stride(1) and out.stride(0) == sq * out.stride(1))
     scale = head_dim ** -0.5 if scale is None else scale
-    if "attention" in SKIP:
-        return out
     need = int(lib.onedc_attention_ws_floats(b, heads, head_dim, sq, skv))
     ws = _attn_ws(q.device, need) if need > 0 else None
     e0 = _prof_begin()
@@ -378,8 +377,11 @@ def gn_arena_reset(device):
     ar = _gn_arena.get(key)
     if ar is None:
         ar = _gn_arena[key] = {"buf": torch.zeros(1 << 22, device=device, dtype=torch.float64), "off": 0, "peak": 0}
-    if ar["off"] > 0:
-        ar["buf"][: ar["off"]].zero_()
+    # zero up to the HIGH-WATER mark of the lane, not just the extent of the last Python-side pass: replays of an
+    # earlier, larger graph dirty the arena without the Python offset knowing
+    ar["peak"] = max(ar["peak"], ar["off"])
+    if ar["peak"] > 0:
+        ar["buf"][: ar["peak"]].zero_()
     ar["off"] = 0
 
 

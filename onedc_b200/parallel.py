@@ -27,6 +27,13 @@ def init_distributed(backend=None):
     return rank, world, local
 
 
+def rank_world():
+    """(rank, world) of the initialised process group, (0, 1) for a single process."""
+    if dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
 def shard(items, rank, world):
     """Static round-robin partition: stream i -> rank i mod world."""
     return [it for i, it in enumerate(items) if i % world == rank]

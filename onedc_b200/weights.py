@@ -279,3 +279,121 @@ def merge_lora(sd, name):
     b = sd[name + ".lora_B.default.weight"].float()
     delta = (b.flatten(1) @ a.flatten(1)).reshape(w.shape)
     return w + LORA_SCALE * delta, sd.get(name + ".base_layer.bias")
+
+
+# ----------------------------------------------------------------------------- nn.Module-shaped loading
+class IncompatibleKeys(tuple):
+    """What torch's load_state_dict returns (the reference prints it, inference.py:92-93)."""
+
+    def __new__(cls, missing_keys, unexpected_keys):
+        self = super().__new__(cls, (missing_keys, unexpected_keys))
+        self.missing_keys, self.unexpected_keys = missing_keys, unexpected_keys
+        return self
+
+    def __repr__(self):
+        if not self.missing_keys and not self.unexpected_keys:
+            return "<All keys matched successfully>"
+        return f"IncompatibleKeys(missing_keys={self.missing_keys}, unexpected_keys={self.unexpected_keys})"
+
+
+class LazyNet:
+    """Weight handling of a kernel-launch network, shaped like torch.nn.Module where the reference touches it
+    (src/inference.py:69-72,87-93): construction without weights, `load_state_dict(sd, strict=True)`, `eval()`.
+
+    The kernel-layout weights (LoRA merged, epilogue permutations, bf16) are packed by `_build(sd)`; packing ~1 G
+    parameters takes seconds, so it is deferred until the weights are known: `load_state_dict` builds at once, and a
+    network that is used without ever being loaded builds itself from the seed-0 random initialisation (the analogue
+    of a freshly constructed nn.Module).  Subclasses define `_spec()`, `_build(sd)` and `IGNORED_PREFIXES`, the
+    checkpoint keys that belong to parts of the reference module that are not on the decode path."""
+
+    IGNORED_PREFIXES = ()
+
+    def _lazy_init(self, state_dict=None):
+        d = self.__dict__
+        d["_pending_sd"], d["_built"], d["_on_load"], d["weights_version"] = state_dict, False, [], 0
+
+    def _ensure(self):
+        if not self.__dict__["_built"]:
+            sd = self.__dict__["_pending_sd"]
+            if sd is None:
+                sd = random_state_dict(self._spec(), 0)
+            self.__dict__["_pending_sd"] = None
+            self._build(sd)
+            self.__dict__["_built"] = True
+        return self
+
+    def __getattr__(self, name):
+        # reached only when normal lookup fails: attributes created by _build() before the first use
+        d = self.__dict__
+        if not name.startswith("__") and "_built" in d and not d["_built"]:
+            self._ensure()
+            if name in self.__dict__:
+                return self.__dict__[name]
+        raise AttributeError(f"{type(self).__name__!s} has no attribute {name!r}")
+
+    def load_state_dict(self, state_dict, strict=True):
+        spec = {n: shape for n, shape, _, _ in self._spec()}
+        missing = [n for n in spec if n not in state_dict]
+        unexpected = [k for k in state_dict if k not in spec and not k.startswith(tuple(self.IGNORED_PREFIXES))]
+        errors = [f"size mismatch for {n}: checkpoint {tuple(state_dict[n].shape)}, model {spec[n]}"
+                  for n in spec if n in state_dict and tuple(state_dict[n].shape) != spec[n]]
+        if strict and missing:
+            errors.append("Missing key(s) in state_dict: " + ", ".join(repr(k) for k in missing[:8])
+                          + (" ..." if len(missing) > 8 else ""))
+        if strict and unexpected:
+            errors.append("Unexpected key(s) in state_dict: " + ", ".join(repr(k) for k in unexpected[:8])
+                          + (" ..." if len(unexpected) > 8 else ""))
+        if errors:
+            raise RuntimeError(f"Error(s) in loading state_dict for {type(self).__name__}:\n\t" + "\n\t".join(errors))
+        sd = {n: state_dict[n] for n in spec if n in state_dict}
+        if missing:                                   # strict=False: absent tensors keep the seed-0 initialisation
+            init = random_state_dict([e for e in self._spec() if e[0] in set(missing)], 0)
+            sd.update(init)
+        self.__dict__["_pending_sd"] = None
+        self._build(sd)
+        self.__dict__["_built"] = True
+        self.__dict__["weights_version"] += 1
+        for cb in self.__dict__["_on_load"]:
+            cb()
+        return IncompatibleKeys(missing, unexpected)
+
+    def eval(self):
+        return self
+
+    def train(self, mode=True):
+        assert not mode, "onedc_b200 is inference only"
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def requires_grad_(self, flag=False):
+        return self
+
+
+def load_checkpoint_file(path, map_location="cpu"):
+    """safetensors or torch file -> state dict (src/utils.py load_safetensor equivalent)."""
+    if str(path).endswith(".safetensors"):
+        from safetensors import safe_open
+        with safe_open(path, framework="pt", device=map_location) as f:
+            return {k: f.get_tensor(k) for k in f.keys()}
+    import torch as _t
+    return _t.load(path, map_location=map_location)
+
+
+_VAE_LEGACY = {".query.": ".to_q.", ".key.": ".to_k.", ".value.": ".to_v.", ".proj_attn.": ".to_out.0."}
+
+
+def vae_decoder_state_dict(sd):
+    """Decode-side subset of an SD-VAE checkpoint in diffusers naming (older files name the mid attention
+    query/key/value/proj_attn with 1x1-conv shaped weights)."""
+    out = {}
+    for k, v in sd.items():
+        if not (k.startswith("decoder.") or k.startswith("post_quant_conv.")):
+            continue
+        for a, b in _VAE_LEGACY.items():
+            k = k.replace(a, b)
+        if ".attentions." in k and k.endswith(".weight") and v.dim() == 4:
+            v = v[:, :, 0, 0]
+        out[k] = v
+    return out

@@ -106,7 +106,7 @@ class CodecOracle:
         n = self.nets
         scales, means = common_params.chunk(2, 1)
         common_red = n.y_spatial_prior_reduction(common_params)
-        masks = E.four_part_masks(*means.shape)
+        masks = [m.to(means.device) for m in E.four_part_masks(*means.shape)]
         y_hat = None
         for k in range(4):
             if k > 0:

@@ -524,4 +524,4 @@ class VAEOracle(nn.Module):
         self.decoder = _VAEDecoder(4, attn_patch)
 
     def forward(self, latents):
-        return self.decoder(self.post_quant_conv(latents / 0.18215))
+        return self.decoder(self.post_quant_conv(1 / 0.18215 * latents))     # model...py:186, as written there

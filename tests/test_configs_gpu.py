@@ -73,3 +73,28 @@ def test_config5_2048(model):
     t2 = time.perf_counter()
     print(f"2048x2048: first decode (graph capture) {t1 - t0:.2f} s, replay {1e3 * (t2 - t1):.1f} ms, stream {len(stream)} B")
     assert a.shape == (1, 3, 2048, 2048) and bool(torch.isfinite(a).all()) and torch.equal(a, b)
+
+
+def test_large_batch_decodes_streams_made_at_batch_one(model):
+    """A stream is encoded at batch 1 (compress_synthetic) and decoded inside a batch of 10: at this size the default
+    igemm plan of the 3x3 convs flips to the column-copy tile (10 x 18 tiles > 148 SMs), which changes the fp32 summation
+    order.  The entropy-parameter layers are pinned to a batch-independent plan, so indices, symbols and y_hat must stay
+    bit-identical -- a single flipped CDF index would desynchronise the rANS decoder."""
+    from onedc_b200 import bitstream
+    B, H, W = 10, 768, 768
+    encs, streams = [], []
+    for i in range(3):
+        tr = []
+        s, _ = model.codec_model.compress_synthetic(H, W, seed=300 + i, trace=tr)
+        encs.append(tr)
+        streams.append(s)
+    batch = [streams[i % 3] for i in range(B)]
+    ds = [bitstream.decode_i(s) for s in batch]
+    dec = []
+    model.codec_model._decompress_batch([d["bit_stream_y"] for d in ds], [d["bit_stream_z"] for d in ds], H, W, dec)
+    for k in range(4):
+        for i in range(B):
+            e = encs[i % 3][k]
+            assert torch.equal(dec[k]["idx"][i].view(-1), e["idx"].view(-1)), f"step {k} image {i}: indices differ"
+            assert torch.equal(dec[k]["sym"][i].view(-1), e["sym"].view(-1)), f"step {k} image {i}: symbols differ"
+            assert torch.equal(dec[k]["y_hat"][i], e["y_hat"][0]), f"step {k} image {i}: y_hat differs"

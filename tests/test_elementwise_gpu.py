@@ -178,6 +178,32 @@ def test_quantize_residual_roundtrip(cuda):
     assert (enc.float() - y.float()).abs().max().item() <= 0.5 + 0.07     # half a quantisation step + bf16 rounding
 
 
+@pytest.mark.parametrize("h,w,seed", [(16, 16, 31), (5, 7, 32)])
+def test_quantize_residual_matches_reference_bf16_golden(cuda, h, w, seed):
+    """E1 on the device: symbols and y_hat of the encode twin vs the REFERENCE process_with_mask / quant /
+    combine_for_writing (compression_model.py:87-93,224-239,296-301) run on bf16 tensors in the build container
+    (tests/golden/gen_golden_generator.py): round half to even of the bf16 residual, bit-exact, ties included."""
+    import os
+    import sys
+    import numpy as np
+    from onedc_b200 import ops
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold)
+    from gen_golden_generator import bf16_twin_inputs
+    g = np.load(os.path.join(gold, "encode_twin_bf16.npz"))
+    y, means = bf16_twin_inputs(h, w, seed)                                   # NCHW bf16 (CPU, seeded)
+    y_d = y.permute(0, 2, 3, 1).contiguous().to(cuda)
+    m_d = means.permute(0, 2, 3, 1).contiguous().to(cuda)
+    y_hat = torch.full((1, h, w, 128), 7.0, device=cuda, dtype=torch.bfloat16)
+    sym = torch.empty((1, 32, h, w), device=cuda, dtype=torch.int16)
+    for k in range(4):
+        ops.quantize_residual(y_d, m_d, sym, y_hat, k)
+        assert np.array_equal(sym.cpu().numpy().reshape(-1), g[f"sym_{h}x{w}"][k]), f"step {k}: symbols != reference"
+    ref_y_hat = torch.from_numpy(g[f"y_hat_{h}x{w}"]).view(torch.bfloat16)    # NCHW
+    assert torch.equal(y_hat.cpu().permute(0, 3, 1, 2), ref_y_hat)
+    assert (np.abs(g[f"sym_{h}x{w}"]) > 8).any()
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout,two", [(1, 32, 32, 128, 128, False), (2, 64, 48, 128, 256, False), (1, 96, 96, 64, 512, False),
                                                 (1, 24, 24, 256, 320, True), (2, 96, 96, 64, 320, False), (1, 48, 48, 128, 640, True),
                                                 (1, 40, 24, 64, 1280, False), (1, 24, 24, 1280, 1280, False), (1, 12, 12, 1280, 512, True)])

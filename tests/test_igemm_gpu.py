@@ -279,3 +279,19 @@ def test_tap_expanded_small_cout_conv(cuda, n, h, w, cin, cout, planar, with_res
     assert out.dtype == torch.float32
     _close(out, ref, tol=2e-3)
     assert torch.equal(tc(x, res=res, planar=planar).reshape(-1), (out if not planar else out.permute(0, 3, 1, 2)).reshape(-1))
+
+
+@pytest.mark.parametrize("h,w,cin,cout,k", [(48, 48, 128, 128, 3), (24, 24, 128, 128, 3), (48, 48, 256, 1024, 1), (12, 12, 128, 512, 1)])
+def test_deterministic_plan_is_batch_independent(cuda, h, w, cin, cout, k):
+    """Layers that feed the entropy parameters are launched with det=True: no split-K, no column-copy / transposed tile,
+    so the fp32 summation order of every output element -- hence every bf16 bit of the scales -- is the same whether the
+    image is decoded alone or inside a batch large enough to flip the default plan (n_img * tiles > SM count)."""
+    from onedc_b200 import ops
+    nb = 12
+    x = _mk((nb, h, w, cin), cuda, 11)
+    wt = _mk((cout, cin, k, k), "cpu", 12, scale=(cin * k * k) ** -0.5).float()
+    cw = ops.ConvW(wt, _mk((cout,), "cpu", 13).float(), cuda)
+    batched = ops.igemm(x, cw, det=True)
+    for i in (0, 5, nb - 1):
+        single = ops.igemm(x[i:i + 1].contiguous(), cw, det=True)
+        assert torch.equal(single[0], batched[i]), "deterministic plan: batched result differs from the single-image one"
