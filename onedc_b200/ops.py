@@ -265,7 +265,7 @@ def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None
         ws, cnt = _splitk_buffers(x.device)
         d.splitk_ws, d.splitk_ws_floats, d.splitk_counters, d.splitk_max_tiles = ws.data_ptr(), ws.numel(), cnt.data_ptr(), cnt.numel()
     acc = None
-    if stats is not False and GN_FUSED and d.impl == 0:
+    if stats is not False and GN_FUSED and d.impl in (0, 2):      # 2 = planning only: same decisions as the real launch
         # stats=True: new accumulator slice; stats=<tensor>: keep accumulating into it (the 4 phases of an UpConv).
         # Per-GROUP sums when a 32-column chunk holds whole groups (4/8/16/32 channels per group), else per-CHANNEL
         # sums (UNet widths 320/640/1280: 10/20/40 channels per group), which also serve channel concatenations.

@@ -102,3 +102,34 @@ def test_flash_launch_plans(cuda, b, heads, d, sq, skv, plan):
         assert torch.equal(out, out2)
     finally:
         L.onedc_attention_set_plan(0, 0)
+
+
+@pytest.mark.parametrize("d,skv", [(40, 1024), (80, 640), (160, 300)])
+def test_flash_lazy_rescale_stress(cuda, d, skv):
+    """The exponent reference of the online softmax only moves when a block maximum exceeds it by more than 2^8.  Scores
+    here are large (|s| up to ~60 after scaling) and the keys are ordered so that the row maximum keeps growing from
+    block to block for half of the rows and falls for the other half: many rescales, P values up to 2^8, reference
+    maxima far below / above the final one."""
+    from onedc_b200 import ops
+    b, heads, sq = 1, 4, 256
+    c = heads * d
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn((b, sq, c), generator=g)
+    k = torch.randn((b, skv, c), generator=g) * 0.3
+    ramp = torch.linspace(-1.0, 1.0, skv)[None, :, None]                    # keys later in the sequence align more with u
+    u = torch.randn((1, 1, c), generator=g)
+    k = k + 3.0 * ramp * u
+    q[:, : sq // 2] += 1.5 * u                                               # rows that follow the ramp
+    q[:, sq // 2:] -= 1.5 * u                                                # rows that oppose it
+    v = torch.randn((b, skv, c), generator=g)
+    q, k, v = (t.to(torch.bfloat16).to(cuda) for t in (q, k, v))
+    out = torch.zeros((b, sq, c), device=cuda, dtype=torch.bfloat16)
+    ops.attention(q, k, v, out, heads, d)
+    ref = _ref(q, k, v, heads, d)
+    smax = float((q.float().view(b, sq, heads, d).transpose(1, 2) @ k.float().view(b, skv, heads, d).transpose(1, 2).transpose(2, 3)).abs().max()) * d ** -0.5
+    assert smax > 20, f"test should produce large scores (got {smax})"
+    err = (out.float() - ref).abs().max().item()
+    assert err < 3e-2, f"max abs err {err}"
+    chk = torch.zeros_like(out)
+    ops.attention(q, k, v, chk, heads, d, impl=1)                           # SIMT checker agrees too
+    assert (out.float() - chk.float()).abs().max().item() < 3e-2

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from onedc_b200 import ops
 dev = torch.device("cuda:0")
-for S, d, skv in ((9216, 40, 9216), (2304, 80, 2304), (576, 160, 576), (9216, 40, 144)):
+for S, d, skv in ((9216, 40, 9216), (2304, 80, 2304), (576, 160, 576), (9216, 40, 144), (65536, 40, 65536)):
     heads = 8
     c = heads * d
     q = torch.randn((1, S, c), device=dev).to(torch.bfloat16)
