@@ -77,12 +77,12 @@ def test_unfused_matches_sdpa(cuda, b, heads, d, s):
     assert err < 2e-2, f"max abs err {err}"
 
 
-@pytest.mark.parametrize("plan", [(1, 1), (2, 3), (1, 3), (2, 4)])
+@pytest.mark.parametrize("plan", [(32, 1), (64, 1), (32, 3), (64, 3), (64, 4), (32, 4)])
 @pytest.mark.parametrize("b,heads,d,sq,skv", [(1, 8, 40, 2304, 5000), (2, 8, 40, 1152, 1152), (1, 8, 64, 2304, 1100), (1, 8, 80, 576, 2304)])
 def test_flash_launch_plans(cuda, b, heads, d, sq, skv, plan):
-    """The non-default launch plans: one S buffer / three CTAs per SM, and the key range split over several CTAs per
-    query tile (fp32 partial O + running max / sum, merged by attention_merge_kernel): ragged last block, batch > 1,
-    d = 64 and a head_dim that cannot take the one-buffer variant."""
+    """Every launch plan: 32- and 64-key blocks (four / two CTAs per SM), and the key range split over several CTAs per
+    query tile (fp32 partial O + reference max / sum, merged by attention_merge_kernel): ragged last block, batch > 1,
+    d = 64 and a head_dim whose 32-key variant needs 256 tensor-memory columns."""
     from onedc_b200 import lib, ops
     L = lib.load()
     L.onedc_attention_set_plan(*plan)
