@@ -131,6 +131,11 @@ typedef struct {
    * for every layer that feeds the entropy parameters (hyper-synthesis, prior nets): encoder and decoder must see
    * bit-identical scales (compression_model.py:369-407), also when one of them batches. */
   int32_t deterministic;
+  /* 1 = w_ptr holds one more [cout][ktot] matrix behind its taps, the identity (cout == channels of `res`).  The kernel
+   * may then add a bf16 residual on the tensor core: the residual tensor becomes one more K chunk group of the centre
+   * pixel multiplied by that identity (exact: bf16 x 1.0 accumulated in fp32), loaded by TMA in the main loop instead of
+   * by 2-byte loads in the epilogue.  Used for the transposed tile (cout <= 128) with no activation. */
+  int32_t w_identity_tap;
 } onedc_igemm_desc;
 
 /* diagnostics: when set (device pointer to 148 x 16 int64, zeroed by the caller) every igemm CTA records clock

@@ -68,11 +68,32 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 }
 #endif
 
+// GELU (exact, erf form) for bf16 outputs.  erf(z) = z * P(z^2) on |z| <= 3.2 (degree-8 polynomial in z^2, fitted for
+// absolute error: 6.2e-5 in fp32 Horner form; erf(3.2) = 1 - 6e-6 beyond), i.e. 11 FMA-pipe instructions instead of the ~30 of
+// erff.  The GEGLU epilogue of the UNet's feed-forward GEMMs (K = 320..1280, 128 x 256 accumulators per tile) was bound by
+// exactly that: 10 k clocks of epilogue per tile against 2.6 k clocks of MMA.  The error in gelu(x) is below 0.5 |x| 6.2e-5,
+// 1/60 of a bf16 half-ulp of the result.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fminf(fmaxf(x * 0.70710678118654752f, -3.2f), 3.2f);
+  const float t = z * z;
+  float p = 2.804641676e-08f;
+  p = fmaf(p, t, -1.468352581e-06f);
+  p = fmaf(p, t, 3.372799397e-05f);
+  p = fmaf(p, t, -4.514517528e-04f);
+  p = fmaf(p, t, 3.961231007e-03f);
+  p = fmaf(p, t, -2.439187257e-02f);
+  p = fmaf(p, t, 1.101094308e-01f);
+  p = fmaf(p, t, -3.747264627e-01f);
+  p = fmaf(p, t, 1.128165502e+00f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, z * p, hx);
+}
+
 __device__ __forceinline__ float act_apply(float v, int act, float slope) {
   switch (act) {
     case ACT_LRELU: return v > 0.f ? v : v * slope;
     case ACT_SILU: return v / (1.f + __expf(-v));
-    case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+    case ACT_GELU: return gelu_erf(v);
     default: return v;
   }
 }

@@ -19,6 +19,15 @@ __device__ __constant__ int kXor[4] = {0, 3, 2, 1};
 // of one plane.  The tile is swizzled (8-pixel group index XOR vector index) so that both phases are conflict-free.
 // The lookup uses the compact table: only bf16 patterns in [lo, hi) have an index other than 0 / 255
 // (lo = first pattern with index > 0, hi = first pattern with index 255), ~1.2 KB instead of 64 KB.
+// 16-byte read-only load that asks L2 for 64 bytes only.  The active slice of a pixel is 64 contiguous bytes out of its 256 or
+// 512; with the default 128-byte promotion every slice dragged its neighbour out of DRAM as well (ncu: 1074 MB read for
+// 537 MB of scales).
+__device__ __forceinline__ uint4 ldg_l2_64(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
 template <int C4>
 __global__ void __launch_bounds__(128) scale_to_index_kernel(const __nv_bfloat16* scales, long long ld, const uint8_t* lut,
                                                              int lo, int hi, int16_t* idx_out, int step, int h, int w) {
@@ -42,7 +51,7 @@ __global__ void __launch_bounds__(128) scale_to_index_kernel(const __nv_bfloat16
     if (okp[it]) {
       const int y = (int)p / w, x = (int)p - y * w;      // h * w < 2^31 (checked by the host wrapper)
       const int g = (2 * (y & 1) + (x & 1)) ^ kXor[step];
-      q[it] = __ldg(reinterpret_cast<const uint4*>(scales + ((long long)n * hw + p) * ld + g * C4) + v);
+      q[it] = ldg_l2_64(reinterpret_cast<const uint4*>(scales + ((long long)n * hw + p) * ld + g * C4) + v);
     }
   }
   for (int i = threadIdx.x; i < span; i += 128) tab[i] = __ldg(lut + lo + i);
@@ -81,22 +90,43 @@ __global__ void __launch_bounds__(128) scale_to_index_kernel(const __nv_bfloat16
   }
 }
 
-// generic elementwise build_indexes (int32 out)
-__global__ void build_indexes_kernel(const void* scales, int dtype, const uint8_t* lut, const float* thr, int32_t* out,
-                                     long long n) {
+// generic elementwise build_indexes (int32 out).  bf16 input: the 64 KB pattern table is staged in shared memory once per block
+// (persistent grid-stride blocks), then 8 scales (one 16-byte load) -> 8 table bytes -> two 16-byte stores per thread.
+// (One scalar 2-byte load, one global table byte and one 4-byte store per thread reached 42 % of HBM.)
+__global__ void __launch_bounds__(512) build_indexes_kernel(const void* scales, int dtype, const uint8_t* lut, const float* thr, int32_t* out,
+                                                            long long n) {
+  extern __shared__ __align__(16) uint8_t tab[];
   pdl_wait();
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    if (dtype == DT_BF16) {
-      out[i] = __ldg(lut + reinterpret_cast<const uint16_t*>(scales)[i]);
-    } else {
-      const float s = reinterpret_cast<const float*>(scales)[i];
-      int lo = 0, hi = 255;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (s >= __ldg(thr + mid)) lo = mid + 1; else hi = mid;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  if (dtype == DT_BF16) {
+    for (int i = threadIdx.x; i < 65536 / 16; i += blockDim.x) reinterpret_cast<uint4*>(tab)[i] = __ldg(reinterpret_cast<const uint4*>(lut) + i);
+    __syncthreads();
+    const bool vec = (reinterpret_cast<uintptr_t>(scales) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+    const long long nv = vec ? n >> 3 : 0;
+    for (long long i = tid; i < nv; i += nth) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(scales) + i);
+      const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+      int r[8];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        r[2 * j] = tab[wd[j] & 0xFFFFu];
+        r[2 * j + 1] = tab[wd[j] >> 16];
       }
-      out[i] = lo;
+      int4* o = reinterpret_cast<int4*>(out) + 2 * i;
+      __stcs(o, make_int4(r[0], r[1], r[2], r[3]));
+      __stcs(o + 1, make_int4(r[4], r[5], r[6], r[7]));
     }
+    for (long long i = nv * 8 + tid; i < n; i += nth) out[i] = tab[reinterpret_cast<const uint16_t*>(scales)[i]];
+    return;
+  }
+  for (long long i = tid; i < n; i += nth) {
+    const float s = reinterpret_cast<const float*>(scales)[i];
+    int lo = 0, hi = 255;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s >= __ldg(thr + mid)) lo = mid + 1; else hi = mid;
+    }
+    out[i] = lo;
   }
 }
 
@@ -131,8 +161,8 @@ __global__ void __launch_bounds__(128) dequant_kernel(int16_t* sym, const __nv_b
       const int y = (int)p / w, x = (int)p - y * w;      // h * w < 2^31 (checked by the host wrapper)
       gq[it] = (2 * (y & 1) + (x & 1)) ^ kXor[step];
       const long long pix = (long long)n * hw + p;
-      mq[it] = __ldg(reinterpret_cast<const uint4*>(means + pix * means_ld + gq[it] * C4) + v);
-      if (MODE == 1) yq[it] = __ldg(reinterpret_cast<const uint4*>(yin + pix * yin_ld + gq[it] * C4) + v);
+      mq[it] = ldg_l2_64(reinterpret_cast<const uint4*>(means + pix * means_ld + gq[it] * C4) + v);
+      if (MODE == 1) yq[it] = ldg_l2_64(reinterpret_cast<const uint4*>(yin + pix * yin_ld + gq[it] * C4) + v);
     }
   }
   if (MODE == 0 && sym != nullptr) {
@@ -229,58 +259,90 @@ __global__ void fsq_codes_kernel(const int32_t* idx, __nv_bfloat16* out, long lo
 }
 
 // ------------------------------------------------------------------------------------------------
-// depthwise 3x3, pad 1, NHWC bf16; weights fp32 [9][C], bias fp32 [C]
-__global__ void __launch_bounds__(256) dwconv3x3_kernel(const __nv_bfloat16* x, const float* w9c, const float* bias,
-                                                        __nv_bfloat16* out, int n_img, int h, int w, int c) {
+// depthwise 3x3, pad 1, NHWC bf16; weights fp32 [9][C], bias fp32 [C].
+// Thread = (4-channel vector, column x) of one strip of output rows: it keeps the 3 x 3 window of its column in registers
+// and slides it down the strip, so every output costs 3 new 8-byte loads (row y+1 at x-1, x, x+1; two of the three are the
+// neighbouring threads' centre columns and hit L1) instead of 9 loads + 18 weight loads, and the nine weight vectors are read
+// once per strip.  4 channels per thread: nine fp32 weight vectors + the window fit 80 registers, three blocks per SM (with 8
+// channels per thread the kernel needed 138 registers, ran one block per SM and reached 21 % of HBM; round 1's one thread
+// per output vector with nine loads each: 18 %).  The strip height is chosen by the host: 16 rows for big tensors, 2..4 for
+// the codec's 48 x 48 planes, which need the threads more than the reuse.
+__global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const __nv_bfloat16* x, const float* w9c, const float* bias,
+                                                           __nv_bfloat16* out, int n_img, int h, int w, int c, int kDwRows) {
   pdl_wait();
-  const int nvec = c >> 3;
+  const int nvec = c >> 2;
+  const int strips = (h + kDwRows - 1) / kDwRows;
+  const long long total = (long long)n_img * strips * w * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    long long t = i / nvec;
+    const int xx = (int)(t % w);
+    t /= w;
+    const int strip = (int)(t % strips);
+    const int n = (int)(t / strips);
+    const int y0 = strip * kDwRows, y1 = y0 + kDwRows < h ? y0 + kDwRows : h;
+    float4 wk[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) wk[k] = __ldg(reinterpret_cast<const float4*>(w9c + k * c) + v);
+    const float4 bs = __ldg(reinterpret_cast<const float4*>(bias) + v);
+    const bool okl = xx > 0, okr = xx + 1 < w;
+    auto load_row = [&](const int iy, uint2* r) {              // r[0..2] = columns x-1, x, x+1 of row iy (zeros outside)
+      r[0] = r[1] = r[2] = make_uint2(0, 0);
+      if (iy >= 0 && iy < h) {
+        const uint2* rp = reinterpret_cast<const uint2*>(x + (((long long)n * h + iy) * w + xx) * c) + v;
+        r[1] = __ldg(rp);
+        if (okl) r[0] = __ldg(rp - nvec);
+        if (okr) r[2] = __ldg(rp + nvec);
+      }
+    };
+    uint2 win[3][3];
+    load_row(y0 - 1, win[0]);
+    load_row(y0, win[1]);
+    for (int yy = y0; yy < y1; yy++) {
+      load_row(yy + 1, win[2]);
+      float a0 = bs.x, a1 = bs.y, a2 = bs.z, a3 = bs.w;
+#pragma unroll
+      for (int ky = 0; ky < 3; ky++) {
+#pragma unroll
+        for (int kx = 0; kx < 3; kx++) {
+          const uint2 q = win[ky][kx];
+          const float4 wv = wk[ky * 3 + kx];
+          a0 = fmaf(bf16lo(q.x), wv.x, a0);
+          a1 = fmaf(bf16hi(q.x), wv.y, a1);
+          a2 = fmaf(bf16lo(q.y), wv.z, a2);
+          a3 = fmaf(bf16hi(q.y), wv.w, a3);
+        }
+      }
+      uint2 o;
+      o.x = pack_bf16x2(a0, a1);
+      o.y = pack_bf16x2(a2, a3);
+      reinterpret_cast<uint2*>(out + (((long long)n * h + yy) * w + xx) * c)[v] = o;
+#pragma unroll
+      for (int kx = 0; kx < 3; kx++) {
+        win[0][kx] = win[1][kx];
+        win[1][kx] = win[2][kx];
+      }
+    }
+  }
+}
+
+// nearest 2x upsample, NHWC: thread = one INPUT vector, read once and stored to its four output pixels
+__global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* x, uint4* out, int n_img, int h, int w, int nvec) {
+  pdl_wait();
   const long long total = (long long)n_img * h * w * nvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i % nvec);
     long long pix = i / nvec;
-    const int xx = (int)(pix % w);
+    const int xi = (int)(pix % w);
     const long long t = pix / w;
-    const int yy = (int)(t % h);
+    const int yi = (int)(t % h);
     const int n = (int)(t / h);
-    float acc[8];
-    {
-      const float4* b4 = reinterpret_cast<const float4*>(bias + v * 8);
-      float4 b0 = __ldg(b4), b1 = __ldg(b4 + 1);
-      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
-    }
-#pragma unroll
-    for (int ky = 0; ky < 3; ky++) {
-      const int iy = yy + ky - 1;
-      if (iy < 0 || iy >= h) continue;
-#pragma unroll
-      for (int kx = 0; kx < 3; kx++) {
-        const int ix = xx + kx - 1;
-        if (ix < 0 || ix >= w) continue;
-        uint4 q = __ldg(reinterpret_cast<const uint4*>(x + (((long long)n * h + iy) * w + ix) * c + v * 8));
-        const float4* w4 = reinterpret_cast<const float4*>(w9c + (ky * 3 + kx) * c + v * 8);
-        float4 w0 = __ldg(w4), w1 = __ldg(w4 + 1);
-        acc[0] += bf16lo(q.x) * w0.x; acc[1] += bf16hi(q.x) * w0.y; acc[2] += bf16lo(q.y) * w0.z; acc[3] += bf16hi(q.y) * w0.w;
-        acc[4] += bf16lo(q.z) * w1.x; acc[5] += bf16hi(q.z) * w1.y; acc[6] += bf16lo(q.w) * w1.z; acc[7] += bf16hi(q.w) * w1.w;
-      }
-    }
-    uint4 o;
-    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
-    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
-    reinterpret_cast<uint4*>(out)[i] = o;
-  }
-}
-
-__global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* x, uint4* out, int n_img, int h, int w, int nvec) {
-  pdl_wait();
-  const long long total = (long long)n_img * (2 * h) * (2 * w) * nvec;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % nvec);
-    long long pix = i / nvec;
-    const int xo = (int)(pix % (2 * w));
-    const long long t = pix / (2 * w);
-    const int yo = (int)(t % (2 * h));
-    const int n = (int)(t / (2 * h));
-    out[i] = __ldg(x + (((long long)n * h + (yo >> 1)) * w + (xo >> 1)) * nvec + v);
+    const uint4 q = __ldg(x + i);
+    uint4* o = out + (((long long)n * 2 * h + 2 * yi) * (2 * w) + 2 * xi) * nvec + v;
+    o[0] = q;
+    o[nvec] = q;
+    o[(long long)2 * w * nvec] = q;
+    o[(long long)2 * w * nvec + nvec] = q;
   }
 }
 
@@ -437,7 +499,16 @@ extern "C" int onedc_scale_to_index(const void* scales, int64_t ld, const uint8_
 extern "C" int onedc_build_indexes(const void* scales, int32_t in_dtype, const uint8_t* lut, const float* thresholds,
                                    int32_t* idx_out, int64_t n, void* stream) {
   ONEDC_CHECK((in_dtype == DT_BF16 && lut) || (in_dtype == DT_F32 && thresholds), "build_indexes: missing table");
-  ONEDC_CUDA(launch_k(build_indexes_kernel, ew_blocks(n, 256), 256, 0, (cudaStream_t)stream, scales, in_dtype, lut, thresholds, idx_out, n));
+  static bool attr_done = false;
+  if (!attr_done) {
+    ONEDC_CUDA(cudaFuncSetAttribute(build_indexes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    attr_done = true;
+  }
+  ONEDC_CHECK(in_dtype != DT_BF16 || reinterpret_cast<uintptr_t>(lut) % 16 == 0, "build_indexes: table must be 16-byte aligned");
+  int blocks = ew_blocks(n / 8 + 1, 512);
+  if (in_dtype == DT_BF16 && blocks > 3 * sm_count()) blocks = 3 * sm_count();          // three 64 KB tables per SM, grid-stride
+  ONEDC_CUDA(launch_k(build_indexes_kernel, blocks, 512, in_dtype == DT_BF16 ? 65536 : 0, (cudaStream_t)stream, scales, in_dtype, lut,
+                      thresholds, idx_out, n));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -479,16 +550,20 @@ extern "C" int onedc_fsq_codes(const int32_t* idx, void* out, int64_t n, void* s
 extern "C" int onedc_dwconv3x3(const void* x, const float* w9c, const float* bias, void* out, int32_t n_img, int32_t h,
                                int32_t w, int32_t c, void* stream) {
   ONEDC_CHECK(c % 8 == 0, "dwconv3x3: C must be a multiple of 8");
-  const long long total = (long long)n_img * h * w * (c / 8);
+  ONEDC_CHECK(reinterpret_cast<uintptr_t>(w9c) % 16 == 0 && reinterpret_cast<uintptr_t>(bias) % 16 == 0, "dwconv3x3: weights / bias must be 16-byte aligned");
+  // strip height: halve it until the launch has a few blocks per SM (or the strips are 2 rows)
+  int rows = 16;
+  while (rows > 2 && (long long)n_img * ((h + rows - 1) / rows) * w * (c / 4) < (long long)sm_count() * 1024) rows >>= 1;
+  const long long total = (long long)n_img * ((h + rows - 1) / rows) * w * (c / 4);
   ONEDC_CUDA(launch_k(dwconv3x3_kernel, ew_blocks(total, 256), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, w9c, bias,
-                                                                           (__nv_bfloat16*)out, n_img, h, w, c));
+                                                                           (__nv_bfloat16*)out, n_img, h, w, c, rows));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int onedc_upsample2x(const void* x, void* out, int32_t n_img, int32_t h, int32_t w, int32_t c, void* stream) {
   ONEDC_CHECK(c % 8 == 0, "upsample2x: C must be a multiple of 8");
-  const long long total = (long long)n_img * 4 * h * w * (c / 8);
+  const long long total = (long long)n_img * h * w * (c / 8);
   ONEDC_CUDA(launch_k(upsample2x_kernel, ew_blocks(total, 256), 256, 0, (cudaStream_t)stream, (const uint4*)x, (uint4*)out, n_img, h, w, c / 8));
   ONEDC_CUDA(cudaGetLastError());
   return 0;

@@ -64,6 +64,10 @@ struct IgemmParams {
   // alone saturates the 128 B/clk of shared memory; N = 256 reads 12 KB per 128 clocks.  Accumulator lanes are then
   // output channels and the epilogue stores one bf16 per lane (64 contiguous bytes per warp and pixel).
   int transposed;
+  // residual on the tensor core (column-copy modes): res_chunks 64-channel chunks of the residual tensor (tensor map 1)
+  // follow the K loop as one more column group -- the centre pixel, one "tap" -- whose weights are the identity stored
+  // behind the taps (onedc_igemm_desc.w_identity_tap).  The epilogue then has no residual to load.
+  int res_chunks;
   const uint8_t* pf_ptr;  // optional L2 prefetch hint (the next layer's weights)
   long long pf_bytes;
   // optional per-CTA role timing (onedc_igemm_set_debug): 16 clock counters per CTA, see tools/igemm_roles.py
@@ -122,7 +126,7 @@ __device__ __forceinline__ void epilogue16(const IgemmParams& p, int img, int y,
       if (p.epi_mode == EPI_PAIR_LRELU)
         v[j] = (va > 0.f ? va : 0.1f * va) + (vb > 0.f ? vb : 0.01f * vb);
       else
-        v[j] = va * (0.5f * vb * (1.f + erff(vb * 0.70710678118654752f)));
+        v[j] = va * gelu_erf(vb);
     }
   }
   const long long pix = ((long long)img * p.H + y) * p.W + x;
@@ -286,7 +290,7 @@ __device__ __forceinline__ void epi_finish32(const IgemmParams& p, float* a, con
       for (int i = 0; i < 32; i++) v[i] = __fdividef(v[i], 1.f + __expf(-v[i]));
     } else if (p.act == ACT_GELU) {
 #pragma unroll
-      for (int i = 0; i < 32; i++) v[i] = 0.5f * v[i] * (1.f + erff(v[i] * 0.70710678118654752f));
+      for (int i = 0; i < 32; i++) v[i] = gelu_erf(v[i]);
     }
   } else {
     const float4* ba = reinterpret_cast<const float4*>(bias_a);
@@ -302,7 +306,7 @@ __device__ __forceinline__ void epi_finish32(const IgemmParams& p, float* a, con
         if (p.epi_mode == EPI_PAIR_LRELU)
           v[4 * i + j] = (va > 0.f ? va : 0.1f * va) + (vb > 0.f ? vb : 0.01f * vb);
         else
-          v[4 * i + j] = va * (0.5f * vb * (1.f + erff(vb * 0.70710678118654752f)));
+          v[4 * i + j] = va * gelu_erf(vb);
       }
     }
   }
@@ -486,13 +490,15 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         const TileCoord t = decode_tile(p, item);
         const int n0 = t.n_tile * p.BN;
         const int ay = t.y0 + p.cm_miny;
-        for (int c = 0; c < nch; c++) {
-          const int src = c >= kch0 ? 1 : 0;
-          const int kc = src ? c - kch0 : c;
+        for (int c = 0; c < nch + p.res_chunks; c++) {
+          const bool isres = c >= nch;                     // residual chunk: tensor map 1, centre column, identity "tap"
+          const int src = (isres || c >= kch0) ? 1 : 0;
+          const int kc = isres ? c - nch : (src ? c - kch0 : c);
           const CUtensorMap* ma = src ? &map_a1 : &map_a0;
-          const int kb = (src ? c1_off : 0) + kc * 64;
-          for (int g = 0; g < groups; g++) {
-            const int nt = p.cm_nt[g], ax = t.x0 + p.cm_dx[g];
+          const int kb = isres ? kc * 64 : (src ? c1_off : 0) + kc * 64;
+          const int ng = isres ? 1 : groups;
+          for (int g = 0; g < ng; g++) {
+            const int nt = isres ? 1 : p.cm_nt[g], ax = t.x0 + (isres ? 0 : p.cm_dx[g]);
             mbar_wait_t<TIMED>(a_eb, pa, &w_a);
             if (leader) {
               mbar_expect_tx_a(a_fb, a_sz);
@@ -504,7 +510,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
               sa = 0; pa ^= 1; a_dst = smem0; a_fb = afull0; a_eb = aempty0;
             }
             for (int j = 0; j < nt; j++) {
-              const int tap = p.cm_tap[g][j];
+              const int tap = isres ? p.taps : p.cm_tap[g][j];
               mbar_wait_t<TIMED>(b_eb, pb, &w_b);
               if (leader) {
                 mbar_expect_tx_a(b_fb, b_bytes);
@@ -591,12 +597,14 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
         uint32_t accumulate = 0;
-        for (int c = 0; c < nch; c++) {
-          for (int g = 0; g < groups; g++) {
-            const int nt = p.cm_nt[g];
+        for (int c = 0; c < nch + p.res_chunks; c++) {
+          const bool isres = c >= nch;
+          const int ng = isres ? 1 : groups;
+          for (int g = 0; g < ng; g++) {
+            const int nt = isres ? 1 : p.cm_nt[g];
             mbar_wait_t<TIMED>(a_fb, pa, &w_a);
             for (int j = 0; j < nt; j++) {
-              const uint32_t row_enc = (uint32_t)p.cm_row[g][j] * 64u;           // rows of 8 pixels x 128 B = 1024 B
+              const uint32_t row_enc = (uint32_t)(isres ? -p.cm_miny : p.cm_row[g][j]) * 64u;   // rows of 8 pixels x 128 B = 1024 B
               mbar_wait_t<TIMED>(b_fb, pb, &w_b);
               tc_fence_after();
               if (leader) {
@@ -952,6 +960,10 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           st_img = t.img;
           st_nt = t.n_tile;
         }
+        // (Issuing the tcgen05.ld of the next chunk before the current one is finished -- a tensor-memory load takes ~700
+        // clocks under a running main loop, a third of the epilogue of the small-K layers -- was tried in round 2: the second
+        // register set makes ptxas reschedule the whole kernel and EVERY layer got 10..50 % slower, also the tilings that do
+        // not run this loop.)
         for (int c = member * 32; c < out_cols_tile; c += 64) {
           float a[32], b[32];
           {
@@ -1391,14 +1403,23 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
           // transposed variant for narrow outputs: one 128-channel M tile, N = 32 x 8 pixels
           static const bool transp_on = getenv("ONEDC_TRANSPOSED") == nullptr || getenv("ONEDC_TRANSPOSED")[0] != '0';
           const int tiles32x8 = p.n_img * ((p.H + 31) / 32) * ((p.W + 7) / 8);
+          static const bool res_mma_on = getenv("ONEDC_RES_MMA") == nullptr || getenv("ONEDC_RES_MMA")[0] != '0';
+          const bool res_mma = res_mma_on && d->res != nullptr && d->w_identity_tap && d->res_dtype == DT_BF16 && d->act == ACT_NONE &&
+                               d->a_c[1] == 0 && d->ktot == d->cout && d->res_ld % 8 == 0 &&
+                               reinterpret_cast<uintptr_t>(d->res) % 16 == 0;
           const int cpg_t = d->gn_acc != nullptr && d->gn_groups > 0 ? d->cout / d->gn_groups : 1;
           if (transp_on && !pair && d->cout <= 128 && d->cout >= 64 && p.n_tiles == 1 && d->store_mode == ST_NORMAL &&
-              d->out_dtype == DT_BF16 && (d->res == nullptr || (colmode_all && d->res_dtype == DT_BF16)) &&   // residual: 2-byte
-              // loads per lane and pixel make the epilogue the bottleneck (measured slower than the regular tile)
+              d->out_dtype == DT_BF16 && (d->res == nullptr || res_mma || (colmode_all && d->res_dtype == DT_BF16)) &&
+              // a residual read in the epilogue costs 2-byte loads per lane and pixel and makes the epilogue the bottleneck
+              // (208 us against 141 us for 128 -> 128 at 768 x 768): it goes through the tensor core instead (res_mma)
               (d->act == ACT_NONE || (d->act == ACT_LRELU && d->slope > 0.f && d->slope <= 1.f)) &&
               (colmode_all || tiles32x8 > sm_count()) && (cpg_t & (cpg_t - 1)) == 0 && cpg_t <= 32 &&
               (d->gn_acc == nullptr || d->cout % d->gn_groups == 0)) {
             p.transposed = 1;
+            if (res_mma) {
+              p.res_chunks = (d->cout + 63) / 64;
+              p.res = nullptr;                            // nothing left for the epilogue to add
+            }
             p.TH = 32;
             p.BN = 128;                                   // weight rows per tile (TMA box; rows >= cout are zero-filled)
             p.cm_rows = 32 + maxy - miny;
@@ -1456,16 +1477,19 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
   CUtensorMap ma[2], mb;
   memset(ma, 0, sizeof(ma));
   for (int s = 0; s < 2; s++) {
-    if (d->a_c[s] == 0) {
+    const bool res_map = s == 1 && p.res_chunks > 0;      // the residual as a second activation source (stride 1, cout channels)
+    if (d->a_c[s] == 0 && !res_map) {
       ma[s] = ma[0];
       continue;
     }
-    ONEDC_CHECK(reinterpret_cast<uintptr_t>(d->a_ptr[s]) % 16 == 0, "igemm: A pointer must be 16-byte aligned");
-    const uint64_t S = (uint64_t)d->a_pix_stride[s];
+    const void* a_base = res_map ? d->res : d->a_ptr[s];
+    const int a_ch = res_map ? d->cout : d->a_c[s];
+    ONEDC_CHECK(reinterpret_cast<uintptr_t>(a_base) % 16 == 0, "igemm: A pointer must be 16-byte aligned");
+    const uint64_t S = (uint64_t)(res_map ? d->res_ld : d->a_pix_stride[s]);
     uint64_t dims[5], str[4];
     uint32_t box[5] = {64, (uint32_t)p.TW, 1, (uint32_t)(p.colmode ? p.cm_rows : p.TH), 1};
     if (d->stride == 1) {
-      dims[0] = (uint64_t)d->a_c[s];
+      dims[0] = (uint64_t)a_ch;
       dims[1] = (uint64_t)d->w_in;
       dims[2] = 1;
       dims[3] = (uint64_t)d->h_in;
@@ -1475,7 +1499,7 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
       str[2] = (uint64_t)d->w_in * S * 2;
       str[3] = (uint64_t)d->h_in * d->w_in * S * 2;
     } else {
-      dims[0] = S + (uint64_t)d->a_c[s];
+      dims[0] = S + (uint64_t)a_ch;
       dims[1] = (uint64_t)d->w_in / 2;
       dims[2] = 2;
       dims[3] = (uint64_t)d->h_in / 2;
@@ -1485,12 +1509,12 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
       str[2] = 2 * (uint64_t)d->w_in * S * 2;
       str[3] = (uint64_t)d->h_in * d->w_in * S * 2;
     }
-    int rc = make_tensor_map(&ma[s], d->a_ptr[s], 5, dims, str, box);
+    int rc = make_tensor_map(&ma[s], a_base, 5, dims, str, box);
     if (rc) return rc;
   }
   {
     ONEDC_CHECK(reinterpret_cast<uintptr_t>(d->w_ptr) % 16 == 0, "igemm: W pointer must be 16-byte aligned");
-    const int nz = d->w_batched ? d->n_img : p.taps;
+    const int nz = d->w_batched ? d->n_img : p.taps + (d->w_identity_tap ? 1 : 0);
     uint64_t dims[3] = {(uint64_t)d->ktot, (uint64_t)d->cout, (uint64_t)nz};
     uint64_t str[2] = {(uint64_t)d->w_row_stride * 2, (uint64_t)d->w_z_stride * 2};
     if (nz == 1) str[1] = str[0] * dims[1];

@@ -323,50 +323,68 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(GnSrc s, long long hw,
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, C <= 1280 (<= 5 vectors of 8 per lane), bf16 in / bf16 out.
+// LayerNorm, bf16 in / bf16 out, C <= 1280.  LPR lanes share a row and each holds up to five 16-byte vectors of it, so a
+// warp works on 32 / LPR rows at once: LPR = 8 for C <= 320 (the UNet's 9216 x 320 token matrix: every lane busy, where
+// one warp per row left 24 of 32 lanes idle in the second round), 16 for C <= 640, 32 above.  Warps walk the rows
+// grid-stride, so a big matrix is a few resident waves instead of 100 k eight-row blocks.
+template <int LPR>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* x, long long ld, long long rows, int c,
                                                         const float* gamma, const float* beta, float eps,
                                                         __nv_bfloat16* out, long long out_ld) {
   pdl_wait();
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31, nvec = c >> 3;
-  float v[5][8];
-  float sum = 0.f;
+  constexpr int RPW = 32 / LPR;                                      // rows per warp and pass
+  const int lane = threadIdx.x & 31, sub = lane % LPR, rsel = lane / LPR;
+  const int nvec = c >> 3;
+  const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (long long)gridDim.x * 8;
+  const float inv_c = 1.f / (float)c;
+  for (long long row = warp0 * RPW + rsel; row - rsel < rows; row += nwarps * RPW) {
+    const bool rok = row < rows;
+    uint4 q[5];
 #pragma unroll
-  for (int i = 0; i < 5; i++) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      load8(x, DT_BF16, row * ld + vi * 8, v[i]);
-#pragma unroll
-      for (int j = 0; j < 8; j++) sum += v[i][j];
+    for (int i = 0; i < 5; i++) {
+      const int vi = sub + i * LPR;
+      q[i] = make_uint4(0, 0, 0, 0);
+      if (rok && vi < nvec) q[i] = __ldg(reinterpret_cast<const uint4*>(x + row * ld) + vi);
     }
-  }
+    float v[5][8];
+    float sum = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / (float)c;
-  float sq = 0.f;
+    for (int i = 0; i < 5; i++) {
+      unpack8(q[i], v[i]);
 #pragma unroll
-  for (int i = 0; i < 5; i++) {
-    if (lane + i * 32 < nvec) {
+      for (int j = 0; j < 8; j++) sum += v[i][j];                    // vectors beyond C are zeros
+    }
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const float d = v[i][j] - mean;
-        sq += d * d;
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_c;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+      if (sub + i * LPR < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float d = v[i][j] - mean;
+          sq += d * d;
+        }
       }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq / (float)c + eps);
+    for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * inv_c + eps);
 #pragma unroll
-  for (int i = 0; i < 5; i++) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      float y[8];
+    for (int i = 0; i < 5; i++) {
+      const int vi = sub + i * LPR;
+      if (rok && vi < nvec) {
+        const float4* g4 = reinterpret_cast<const float4*>(gamma + vi * 8);
+        const float4* b4 = reinterpret_cast<const float4*>(beta + vi * 8);
+        const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 1), b0 = __ldg(b4), b1 = __ldg(b4 + 1);
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float y[8];
 #pragma unroll
-      for (int j = 0; j < 8; j++) y[j] = (v[i][j] - mean) * rstd * gamma[vi * 8 + j] + beta[vi * 8 + j];
-      store8_bf16(out, row * out_ld + vi * 8, y);
+        for (int j = 0; j < 8; j++) y[j] = (v[i][j] - mean) * rstd * gg[j] + bb[j];
+        store8_bf16(out, row * out_ld + vi * 8, y);
+      }
     }
   }
 }
@@ -482,9 +500,13 @@ extern "C" int onedc_groupnorm_apply(const void* x0, int32_t c0, int64_t ld0, co
 extern "C" int onedc_layernorm(const void* x, int64_t ld, int64_t rows, int32_t c, const float* gamma, const float* beta,
                                float eps, void* out, int64_t out_ld, void* stream) {
   ONEDC_CHECK(c % 8 == 0 && c <= 1280 && ld % 8 == 0 && out_ld % 8 == 0, "layernorm: C must be a multiple of 8, <= 1280");
-  const int blocks = (int)((rows + 7) / 8);
-  ONEDC_CUDA(launch_k(layernorm_kernel, blocks, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, ld, rows, c, gamma, beta, eps,
-                                                             (__nv_bfloat16*)out, out_ld));
+  ONEDC_CHECK(reinterpret_cast<uintptr_t>(gamma) % 16 == 0 && reinterpret_cast<uintptr_t>(beta) % 16 == 0, "layernorm: gamma / beta must be 16-byte aligned");
+  const int lpr = c <= 320 ? 8 : (c <= 640 ? 16 : 32);
+  long long blocks = (rows + 8 * (32 / lpr) - 1) / (8 * (32 / lpr));
+  if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;       // grid-stride beyond a few waves
+  auto kern = lpr == 8 ? layernorm_kernel<8> : (lpr == 16 ? layernorm_kernel<16> : layernorm_kernel<32>);
+  ONEDC_CUDA(launch_k(kern, (int)blocks, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, ld, rows, c, gamma, beta, eps,
+                                                 (__nv_bfloat16*)out, out_ld));
   ONEDC_CUDA(cudaGetLastError());
   return 0;
 }

@@ -31,7 +31,7 @@ class IgemmDesc(C.Structure):
         ("ntaps", C.c_int32), ("tap_dy", C.c_int32 * 9), ("tap_dx", C.c_int32 * 9), ("quad", C.c_int32),
         ("gn_acc", C.c_void_p), ("gn_groups", C.c_int32), ("gn_fused_out", C.c_int32),
         ("prefetch_ptr", C.c_void_p), ("prefetch_bytes", C.c_int64),
-        ("deterministic", C.c_int32),
+        ("deterministic", C.c_int32), ("w_identity_tap", C.c_int32),
     ]
 
 

@@ -81,7 +81,13 @@ class ConvW:
         if pad:
             w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, pad))
         self.ksize, self.cout, self.ktot = k, cout, cin + pad
-        self.w = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin + pad).contiguous().to(device=device, dtype=torch.bfloat16)
+        wk = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin + pad)
+        # 3x3, cout == cin <= 128 (the VAE's 128-channel ResnetBlocks at 768x768): one more "tap" holding the identity, so
+        # that the kernel can add the block's residual on the tensor core (onedc_igemm_desc.w_identity_tap)
+        self.identity_tap = bool(k == 3 and cout == cin + pad and 64 <= cout <= 128 and epi == EPI_PLAIN)
+        if self.identity_tap:
+            wk = torch.cat([wk, torch.eye(cout, cin + pad, dtype=wk.dtype, device=wk.device)[None]], 0)
+        self.w = wk.contiguous().to(device=device, dtype=torch.bfloat16)
         self.bias = None if bias is None else bias.detach().float().contiguous().to(device)
         self.epi, self.bn = epi, bn
         self.ncols = cout // 2 if epi != EPI_PLAIN else cout
@@ -97,6 +103,7 @@ class ConvW:
         self.w = w_taps.contiguous().to(device=device, dtype=torch.bfloat16)
         self.bias = None if bias is None else bias.detach().float().contiguous().to(device)
         self.epi, self.bn, self.ncols, self.taps = EPI_PLAIN, 0, cout, list(taps)
+        self.identity_tap = False
         return self
 
 
@@ -226,6 +233,7 @@ def igemm(x, wt, x2=None, stride=1, act=ACT_NONE, slope=0.01, res=None, out=None
         d.w_row_stride, d.w_z_stride = wt.ktot, wt.cout * wt.ktot
         d.bias = None if wt.bias is None else wt.bias.data_ptr()
         d.epi_mode, d.bn = wt.epi, wt.bn
+        d.w_identity_tap = 1 if getattr(wt, "identity_tap", False) else 0
         ncols = wt.ncols
         if wt.taps is not None:
             d.ntaps = len(wt.taps)

@@ -52,7 +52,7 @@ def test_conv_matches_torch(cuda, n, h, w, cin, cout, k, stride, impl):
     b = _mk((cout,), "cpu", 3).float()
     cw = ops.ConvW(wt, b, cuda)
     out = ops.igemm(x, cw, stride=stride, impl=impl)
-    ref = _ref_conv(x, cw.w.float().reshape(k, k, cout, -1).permute(2, 3, 0, 1)[:, :cin].contiguous(), b.to(cuda), k, stride)
+    ref = _ref_conv(x, cw.w[:k * k].float().reshape(k, k, cout, -1).permute(2, 3, 0, 1)[:, :cin].contiguous(), b.to(cuda), k, stride)
     assert out.shape == ref.shape
     _close(out, ref)
 
@@ -150,7 +150,7 @@ def test_large_layer_shapes(cuda):
         wt = _mk((c, c, 3, 3), "cpu", 2, scale=(9 * c) ** -0.5).float()
         cw = ops.ConvW(wt, None, cuda)
         out = ops.igemm(x, cw)
-        ref = _ref_conv(x, cw.w.float().reshape(3, 3, c, c).permute(2, 3, 0, 1).contiguous(), None, 3, 1)
+        ref = _ref_conv(x, cw.w[:9].float().reshape(3, 3, c, c).permute(2, 3, 0, 1).contiguous(), None, 3, 1)
         _close(out, ref)
 
 
@@ -169,7 +169,7 @@ def test_split_k_small_m_layers(cuda, h, w, cin, cout, two):
     out = ops.igemm(x, cw, x2=x2, res=res)
     out2 = ops.igemm(x, cw, x2=x2, res=res)
     assert torch.equal(out, out2)
-    ref = _ref_conv(x, cw.w.float().reshape(3, 3, cout, ct).permute(2, 3, 0, 1).contiguous(), b.to(cuda), 3, 1, x2) + res.float()
+    ref = _ref_conv(x, cw.w[:9].float().reshape(3, 3, cout, ct).permute(2, 3, 0, 1).contiguous(), b.to(cuda), 3, 1, x2) + res.float()
     _close(out, ref)
     _close(ops.igemm(x, cw, x2=x2, res=res, impl=1), ref)
 
@@ -213,7 +213,7 @@ def test_column_copy_mode_3x3(cuda, n, h, w, cin, cin2, cout):
     cw = ops.ConvW(wt, b, cuda)
     ops.gn_arena_reset(cuda)
     out = ops.igemm(x, cw, x2=x2, res=res, stats=True)
-    ref = _ref_conv(x, cw.w.float().reshape(3, 3, cout, -1).permute(2, 3, 0, 1)[:, :ct].contiguous(), b.to(cuda), 3, 1, x2) + res.float()
+    ref = _ref_conv(x, cw.w[:9].float().reshape(3, 3, cout, -1).permute(2, 3, 0, 1)[:, :ct].contiguous(), b.to(cuda), 3, 1, x2) + res.float()
     _close(out, ref)
     _close(ops.igemm(x, cw, x2=x2, res=res, impl=1), ref)
     assert torch.equal(out, ops.igemm(x, cw, x2=x2, res=res)), "not deterministic"
@@ -228,7 +228,10 @@ def test_column_copy_mode_3x3(cuda, n, h, w, cin, cin2, cout):
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout,two,f32", [(1, 384, 384, 128, 128, False, False), (2, 100, 210, 256, 128, False, False),
-                                                    (1, 256, 256, 64, 96, True, False), (1, 320, 200, 128, 64, False, True)])   # fp32 output: regular tile
+                                                    (1, 256, 256, 64, 96, True, False), (1, 320, 200, 128, 64, False, True),   # fp32 output: regular tile
+                                                    # cout == cin: the residual goes through the tensor core (identity tap)
+                                                    (2, 100, 210, 128, 128, False, False), (1, 300, 203, 64, 64, False, False),
+                                                    (1, 256, 250, 96, 96, False, False)])
 def test_transposed_column_copy_mode(cuda, n, h, w, cin, cout, two, f32):
     """Narrow outputs (cout <= 128) on many tiles run the transposed tile: weights as the M operand, 32x8 pixels as
     N = 256, one bf16 store per lane.  Bias, residual, ragged edges, two sources, fp32 output and the fused GroupNorm
@@ -244,7 +247,7 @@ def test_transposed_column_copy_mode(cuda, n, h, w, cin, cout, two, f32):
     ops.gn_arena_reset(cuda)
     od = torch.float32 if f32 else torch.bfloat16
     out = ops.igemm(x, cw, x2=x2, res=res, stats=True, out_dtype=od)
-    ref = _ref_conv(x, cw.w.float().reshape(3, 3, cout, -1).permute(2, 3, 0, 1)[:, :ct].contiguous(), b.to(cuda), 3, 1, x2) + res.float()
+    ref = _ref_conv(x, cw.w[:9].float().reshape(3, 3, cout, -1).permute(2, 3, 0, 1)[:, :ct].contiguous(), b.to(cuda), 3, 1, x2) + res.float()
     _close(out, ref)
     _close(ops.igemm(x, cw, x2=x2, res=res, impl=1, out_dtype=od), ref)
     assert torch.equal(out, ops.igemm(x, cw, x2=x2, res=res, out_dtype=od)), "not deterministic"

@@ -14,8 +14,8 @@ if os.path.exists(pk):
     peak = json.load(open(pk)).get("hbm_gbs", peak)
 
 
-def timeit(fn, iters=20):
-    for _ in range(3):
+def timeit(fn, iters=int(os.environ.get("EW_ITERS", "20"))):
+    for _ in range(3 if iters > 1 else 1):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
