@@ -76,6 +76,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+_T0 = time.time()
+
+
+def _progress(msg):
+    """Phase marks on stderr (the JSON line on stdout stays alone): where a slow run spends its time."""
+    sys.stderr.write(f"[bench {time.time() - _T0:7.1f} s] {msg}\n")
+    sys.stderr.flush()
+
+
 def _state_dicts():
     from onedc_b200 import weights as W
     return (W.random_state_dict(W.unet_spec(), 0), W.random_state_dict(W.codec_spec(), 0),
@@ -340,6 +349,7 @@ def run_ours(args):
                 out_host[i].copy_(img[0], non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
+    _progress("model built, graphs captured")
     for _ in range(args.warmup):
         step_resident()
     torch.cuda.synchronize()
@@ -359,6 +369,7 @@ def run_ours(args):
     parallel.barrier()
     launches = lib.launch_count() if not use_graphs else gd.launches_res * args.steps
     t_res = parallel.reduce_max(e0.elapsed_time(e1) / 1e3 / args.steps)
+    _progress("resident leg timed")
     # ---- e2e: host bytes -> host image through the public API
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
@@ -373,6 +384,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     t_e2e = parallel.reduce_max((time.perf_counter() - t0) / args.steps)
     parallel.barrier()
+    _progress("e2e leg timed")
     # ---- throughput API: `depth` images in flight per GPU (host rANS of one image under the kernels of another)
     pipe = None
     if use_graphs and args.pipeline > 1 and B == 1:
@@ -390,6 +402,7 @@ def run_ours(args):
         pipe = {"value": len(many) * world * H * W * MP / t_pipe, "unit": "MP/s", "images_per_gpu": len(many),
                 "images_in_flight": args.pipeline, "ms_per_image": t_pipe * 1e3 / len(many),
                 "api": "model.decode_many(streams): host bytes -> host images, host rANS and all copies inside"}
+    _progress("pipelined leg timed")
     clocks = sampler.stop() if rank == 0 else None
     # ---- roofline of the dominant kernel (tcgen05 implicit GEMM, ~420 launches per step).  Its time inside the
     #      timed region is measured live as a DIFFERENCE of CUDA-event timings: the same graph-replayed step with and
@@ -425,6 +438,7 @@ def run_ours(args):
                 at_ms_diff = dt
             g2.release()
             del g2
+    _progress("kernel shares by graph difference done")
     ops.PROFILE = []
     torch.cuda._sleep(int(0.12 * 1.9e9))
     model.decode_resident(z_idx, syms)
@@ -463,6 +477,7 @@ def run_ours(args):
             except Exception as e:                                   # a failed extra must not take the headline line down
                 extras[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
             model.release_graphs()                                   # drop that size's graphs / pools before the next one
+            _progress(f"extra config {name} done")
     if rank != 0:
         return
     pixels = H * W * B * world
@@ -498,7 +513,9 @@ def run_ours(args):
     if extras:
         res["configs"] = extras
     if not args.no_cpu_baseline and world == 1:
+        _progress("GPU work done; CPU baseline (child process, bounded)")
         res["cpu_baseline"] = cpu_baseline_bounded(args)
+        _progress("CPU baseline done")
     print(json.dumps(res))
 
 

@@ -150,11 +150,9 @@ int onedc_igemm(onedc_igemm_desc* d, void* stream);
 /* q: [batch, sq, q_ld] bf16 (head h at columns h*d), k/v: [batch, skv, kv_ld], out: [batch, sq, o_ld] */
 /* ws: fp32 scratch of onedc_attention_ws_floats() elements (0 = none needed) for launches whose key range is split
    over several CTAs per query tile to fill the last wave; NULL disables the split */
-/* overrides the launch plan: key_block 32 / 64 = keys per block (default 0: 32 for head_dim <= 64, where two S buffers
-   and O then fit 128 tensor-memory columns and four CTAs share an SM, else 64); kv_splits 1..4 (default 0 = 1) */
-void onedc_attention_set_plan(int32_t key_block, int32_t kv_splits);
-/* optional phase clocks of one softmax warp per CTA (tools/attn_roles.py): (CTAs * 4 + 12) * 8 int64 counters, NULL turns it off */
-void onedc_attention_set_debug(void* dev_counters);
+/* overrides the launch plan: s_buffers 1 = one S buffer / three CTAs per SM (head_dim <= 64), 2 = two S buffers / two
+   CTAs per SM; kv_splits 1..4; 0 = default (2, 1: measured fastest on B200, see attention.cu) */
+void onedc_attention_set_plan(int32_t s_buffers, int32_t kv_splits);
 int64_t onedc_attention_ws_floats(int32_t batch, int32_t heads, int32_t head_dim, int32_t sq, int32_t skv);
 int onedc_attention(const void* q, int64_t q_ld, const void* k, const void* v, int64_t kv_ld, void* out,
                     int64_t o_ld, int32_t batch, int32_t heads, int32_t head_dim, int32_t sq, int32_t skv,

@@ -66,6 +66,30 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   count_launch();
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+// The same with thread-block clusters of `cluster_x` consecutive CTAs: the hardware only starts a cluster when all of its
+// CTAs can be resident at once, so CTAs that wait for each other (the splits of one split-K tile) cannot be stranded
+// behind kernels of other streams.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_cluster_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                    unsigned cluster_x, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  count_launch();
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 #endif
 
 // GELU (exact, erf form) for bf16 outputs.  erf(z) = z * P(z^2) on |z| <= 3.2 (degree-8 polynomial in z^2, fitted for

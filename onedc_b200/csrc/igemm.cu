@@ -1257,6 +1257,12 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
       p.BN /= 2;
       p.n_tiles = (d->cout + p.BN - 1) / p.BN;
     }
+    // split-K runs at most 8 splits per tile (one cluster): with very few tiles that leaves SMs idle, so halve the N tile
+    // first (same weight traffic, same parked bytes, twice the CTAs)
+    if (will_split && p.BN == 256 && d->cout % 128 == 0 && mt * p.n_tiles * 8 * 2 <= sm_count() + 20) {
+      p.BN = 128;
+      p.n_tiles = (d->cout + p.BN - 1) / p.BN;
+    }
   }
   if (pair) ONEDC_CHECK(d->cout % p.BN == 0, "igemm: pair epilogues need cout %% BN == 0 (cout %d BN %d)", d->cout, p.BN);
   pick_tile(p.H, p.W, &p.TH, &p.TW);
@@ -1348,7 +1354,11 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
         kiters >= 16 && tiles <= d->splitk_max_tiles / 2) {
       int s = sm_count() / tiles;
       if (s > kiters / 8) s = kiters / 8;
-      if (s > 16) s = 16;
+      // The splits of a tile wait for each other (arrival counter), so they are launched as one thread-block cluster:
+      // co-residency is then guaranteed by the hardware.  Without it two split-K kernels of different streams (the
+      // pipelined decoder runs three) could each occupy part of the GPU and spin for CTAs that never get an SM.
+      // 8 is the portable cluster limit; two clusters of 8 one-CTA-per-SM blocks also pack a 16..20-SM GPC, 14 would not.
+      if (s > 8) s = 8;
       while (s > 1 && (long long)tiles * s * 128 * p.BN > d->splitk_ws_floats) s--;
       if (s >= 4) p.splits = s;
     }
@@ -1538,10 +1548,11 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
                                     kSmemBudget + 1024));
     attr_set = true;
   }
+  if (p.splits > 1) ONEDC_CHECK(grid == total_tiles && grid % p.splits == 0, "igemm: split-K grid must hold whole clusters");
   if (p.splits > 1 && p.dbg != nullptr)
-    ONEDC_CUDA(launch_k(igemm_tc_kernel<true, true>, grid, kThreads, smem, stream, ma[0], ma[1], mb, p));
+    ONEDC_CUDA(launch_cluster_k(igemm_tc_kernel<true, true>, grid, kThreads, smem, stream, (unsigned)p.splits, ma[0], ma[1], mb, p));
   else if (p.splits > 1)
-    ONEDC_CUDA(launch_k(igemm_tc_kernel<true, false>, grid, kThreads, smem, stream, ma[0], ma[1], mb, p));
+    ONEDC_CUDA(launch_cluster_k(igemm_tc_kernel<true, false>, grid, kThreads, smem, stream, (unsigned)p.splits, ma[0], ma[1], mb, p));
   else if (p.dbg != nullptr)
     ONEDC_CUDA(launch_k(igemm_tc_kernel<false, true>, grid, kThreads, smem, stream, ma[0], ma[1], mb, p));
   else

@@ -46,7 +46,6 @@ PROTOTYPES = {
     "onedc_igemm": (C.c_int, [C.POINTER(IgemmDesc), _vp]),
     "onedc_igemm_set_debug": (None, [_vp]),
     "onedc_attention_set_plan": (None, [_i32, _i32]),
-    "onedc_attention_set_debug": (None, [_vp]),
     "onedc_attention_ws_floats": (_i64, [_i32, _i32, _i32, _i32, _i32]),
     "onedc_attention": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _i64, _vp]),
     "onedc_groupnorm_ws_floats": (_i64, [_i32, _i64, _i32]),

@@ -104,11 +104,11 @@ def test_library_exports_every_declared_symbol(lib):
 def test_host_side_launch_planning(lib):
     """Pure host functions of the C ABI (no kernel runs): the attention launch plan and its scratch size, the
     GroupNorm workspace size, the switches."""
-    # default plan: no key-range split -> no scratch
+    # default plan: two CTAs per SM, no key-range split -> no scratch
     lib.onedc_attention_set_plan(0, 0)
     assert lib.onedc_attention_ws_floats(1, 8, 40, 9216, 9216) == 0
     try:
-        lib.onedc_attention_set_plan(64, 3)
+        lib.onedc_attention_set_plan(2, 3)
         # 3 splits x (O fp32 + running max + sum) per (batch, query, head)
         assert lib.onedc_attention_ws_floats(1, 8, 40, 9216, 9216) == 3 * 9216 * 8 * (40 + 2)
         # too few key blocks for every split to get work: the plan falls back to fewer splits / none
