@@ -1212,6 +1212,36 @@ static void pick_tile(int H, int W, int* th, int* tw) {
 
 static long long* g_igemm_dbg = nullptr;
 
+// clusters of `size` split-K CTAs (one CTA per SM: 200 KB of shared memory) that the device can hold at once
+static int max_active_clusters(int size) {
+  static int cache[17] = {0};
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (size < 1 || size > 16) return 0;
+  if (cache[size] == 0) {
+    cudaFuncSetAttribute(igemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(size * 64));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBudget + 1024;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)size;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, igemm_tc_kernel<true, false>, &cfg) != cudaSuccess) {
+      cudaGetLastError();
+      n = sm_count() / (size < 4 ? size : (size <= 8 ? 9 : 18));      // conservative guess: 16-SM GPCs
+    }
+    cache[size] = n > 0 ? n : -1;
+  }
+  return cache[size] > 0 ? cache[size] : 0;
+}
+
 static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
   ONEDC_CHECK(d->ksize == 1 || d->ksize == 3, "igemm: ksize must be 1 or 3");
   ONEDC_CHECK(d->stride == 1 || (d->stride == 2 && d->ksize == 3), "igemm: stride 2 needs ksize 3");
@@ -1357,10 +1387,26 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
       // The splits of a tile wait for each other (arrival counter), so they are launched as one thread-block cluster:
       // co-residency is then guaranteed by the hardware.  Without it two split-K kernels of different streams (the
       // pipelined decoder runs three) could each occupy part of the GPU and spin for CTAs that never get an SM.
-      // 8 is the portable cluster limit; two clusters of 8 one-CTA-per-SM blocks also pack a 16..20-SM GPC, 14 would not.
+      // 8 is the portable cluster limit.  A cluster lives inside one GPC (16..20 SMs, one CTA per SM here), so not every
+      // size packs the GPU: the largest split count whose clusters are all resident at once wins (two waves of 7-CTA
+      // clusters cost the 12 x 12 layers +45 %); if none fits, the one with the most resident CTAs.
       if (s > 8) s = 8;
       while (s > 1 && (long long)tiles * s * 128 * p.BN > d->splitk_ws_floats) s--;
-      if (s >= 4) p.splits = s;
+      if (s >= 4) {
+        int best = 0, best_ctas = 0;
+        for (int c = s; c >= 3; c--) {
+          const int cap = max_active_clusters(c);
+          if (cap >= tiles) {
+            best = c;
+            break;
+          }
+          if (cap * c > best_ctas) {
+            best_ctas = cap * c;
+            best = c;
+          }
+        }
+        if (best >= 3) p.splits = best;
+      }
     }
   }
 
