@@ -172,6 +172,46 @@ def test_product_rans_matches_oracle_and_golden(lib):
         ec.set_stream(b"\x01\x00")                               # too short to hold a rANS state
 
 
+def test_product_rans_side_by_side_with_reference_module(lib):
+    """csrc/rans_host.cpp is a rewrite of the reference coder (deliberate deviation): on random streams the
+    reference's own C++ (oracle/_ref/MLCodec_rans, compiled from /root/reference/src/cpp by `make -C oracle ref`) must produce
+    the same bytes from the same symbols and decode the product's bytes to the same symbols, single- and multi-call."""
+    from oracle.ref_import import import_reference, reference_available
+    if not reference_available():
+        pytest.skip("oracle/_ref not built (make -C oracle ref; needs /root/reference)")
+    em = import_reference().entropy_models                        # the reference's own EntropyCoder over its pybind module
+    rec = em.EntropyCoder()
+    rge = em.GaussianEncoder()
+    rge.update(force=True, entropy_coder=rec)
+    from onedc_b200.entropy_models import EntropyCoder, GaussianEncoder
+    ec = EntropyCoder()
+    ge = GaussianEncoder()
+    ge.update(force=True, entropy_coder=ec)
+    rng = np.random.default_rng(7)
+    # (the reference encoder itself dies with "double free or corruption" on a 3-symbol stream; the product's coder handles
+    # those, see test_product_rans_matches_oracle_and_golden)
+    for n, wide, calls in ((64, False, 1), (257, True, 1), (6000, False, 4), (40000, True, 4)):
+        idx = rng.integers(0, 256, n).astype(np.int16)
+        sc = np.exp(np.linspace(np.log(0.11), np.log(64), 256))[idx] * (4.0 if wide else 1.0)
+        sym = np.clip(np.rint(rng.standard_normal(n) * sc), -3000, 3000).astype(np.int16)
+        parts = np.array_split(np.arange(n), calls)
+        ec.reset()
+        rec.reset()
+        for p_ in parts:
+            ec.encode_with_indexes_np(sym[p_], idx[p_], 0)
+            rec.encode_with_indexes_np(sym[p_], idx[p_], rge.cdf_group_index)
+        ec.flush()
+        rec.flush()
+        ours, theirs = ec.get_encoded_stream(), rec.get_encoded_stream()
+        assert ours == theirs, f"n={n}: product bytes differ from the reference coder's"
+        rec.set_stream(ours)
+        back = np.concatenate([np.asarray(rec.decode_stream_np(idx[p_], rge.cdf_group_index)).reshape(-1) for p_ in parts])
+        assert np.array_equal(back, sym), f"n={n}: reference decoder reads the product's stream differently"
+        ec.set_stream(theirs)
+        got = np.concatenate([ec.decode_stream_np(idx[p_], 0) for p_ in parts])
+        assert np.array_equal(got, sym)
+
+
 def test_product_golden_stream_symbols(lib):
     """Host rANS of the product decodes the reference-made golden stream to the reference's symbols."""
     from onedc_b200 import bitstream
