@@ -181,7 +181,7 @@ def test_product_rans_side_by_side_with_reference_module(lib):
         pytest.skip("oracle/_ref not built (make -C oracle ref; needs /root/reference)")
     em = import_reference().entropy_models                        # the reference's own EntropyCoder over its pybind module
     rec = em.EntropyCoder()
-    rge = em.GaussianEncoder()
+    rge = em.GaussianEncoder(distribution="gaussian")            # as the codec builds it (compression_model.py:38)
     rge.update(force=True, entropy_coder=rec)
     from onedc_b200.entropy_models import EntropyCoder, GaussianEncoder
     ec = EntropyCoder()
