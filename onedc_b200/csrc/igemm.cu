@@ -573,6 +573,13 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       o[1] = w_a;
       o[2] = w_b;
     }
+    if (SPLITK) {                 // the two cluster barriers of the split-K epilogue need every thread of the cluster
+      __syncwarp();
+      cluster_arrive();
+      cluster_wait();
+      cluster_arrive();
+      cluster_wait();
+    }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t leader = elect_one();
@@ -681,6 +688,13 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
       o[7] = w_t;
     }
     if (leader) pdl_trigger();    // this CTA's MMAs are all issued: the next kernel may start under our epilogue
+    if (SPLITK) {
+      __syncwarp();
+      cluster_arrive();
+      cluster_wait();
+      cluster_arrive();
+      cluster_wait();
+    }
   } else {
     // ===================== epilogue warps =====================
     // warp w may only touch TMEM lanes 32*(w%4)..+31; the two warps of a quarter interleave 32-column chunks.
@@ -804,18 +818,23 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             tp = now;
           }
         };
-        // ---- split-K (one work item per CTA, all co-resident): park the raw fp32 accumulators, wait until all
-        //      splits of this tile have done so, then reduce a row slice of the tile in split order (deterministic)
-        //      and run the real epilogue on it.  The host only enables this on the vector-store fast layout.
-        // Workspace layout of one parked tile, in float4 units: the rows are cut into the `splits` row slices that the
-        // reduction hands out, and inside a slice the order is [column quad][row].  A warp's 32 rows then store runs of
-        // consecutive 16-byte words (row-major parking issued 32 separate lines per store instruction and ran at
-        // 15 B/clk), and each CTA later reads its slice of every split as one contiguous block.
+        // ---- split-K: the `splits` CTAs of a tile are one thread-block cluster (cluster rank = split).  Every CTA sends the
+        //      rows of its fp32 partial accumulator straight into the shared memory of the CTA that owns them
+        //      (st.shared::cluster into the idle operand ring), the cluster synchronises, and every CTA reduces its row
+        //      slice in split order (deterministic) and runs the real epilogue on it.  (Round 1 parked the partials in an L2
+        //      workspace behind arrival counters: park 2.1-3.8 k + fence 1.6-2.1 k + wait 2.6-3.1 k + bulk fetch 5.5-7.9 k
+        //      clocks per CTA, more than the weight-bound main loop.)  The host only enables this on the vector-store layout.
+        // Receive layout in the owner, in float4 units: [sending split][column quad][row of the slice]: a warp's 32 rows
+        // store runs of consecutive 16-byte words.
         const int bn4 = p.BN >> 2;
-        const int my_s = ((row + 1) * p.splits + 127) / 128 - 1;
+        const int my_s = ((row + 1) * p.splits + 127) / 128 - 1;                   // owner of this thread's row
         const int my_r0 = 128 * my_s / p.splits, my_n = 128 * (my_s + 1) / p.splits - my_r0;
-        float4* wtile = reinterpret_cast<float4*>(p.ws) + (size_t)item * 128 * bn4;
-        float4* wmine = wtile + (size_t)my_r0 * bn4 + (row - my_r0);
+        // 1) every CTA of the cluster is past its main loop (this CTA: tmem_full above): all operand rings are idle
+        cluster_arrive();
+        cluster_wait();
+        phase_mark(12);
+        const uint32_t dst0 = mapa_shared(smem0, (uint32_t)my_s) +
+                              16u * (uint32_t)(split * my_n * bn4 + (row - my_r0));
         for (int c = member * 32; c < p.BN; c += 64) {
           uint32_t r[32];
           tmem_ld32(taddr + c, r);
@@ -823,77 +842,61 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           if (!valid) continue;                       // padding rows of an edge tile are never read back
 #pragma unroll
           for (int i = 0; i < 8; i++)
-            __stcg(wmine + (size_t)((c >> 2) + i) * my_n,
-                   make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
-                               __uint_as_float(r[4 * i + 3])));
+            st_cluster_f4(dst0 + 16u * (uint32_t)(((c >> 2) + i) * my_n), __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                          __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);  // TMEM buffer is free again
-        phase_mark(11);                                // park
-        __threadfence();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        phase_mark(12);                                // fence + barrier
-        if (etid == 0) {
-          const long long t0 = TIMED ? clock64() : 0;
-          atomicAdd(p.counters + tile, 1);
-          volatile int* cnt = p.counters + tile;
-          while (*cnt < p.splits) __nanosleep(40);
-          __threadfence();
-          if (TIMED) p.dbg[(size_t)blockIdx.x * 16 + 10] += clock64() - t0;      // waiting for the other splits
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        phase_mark(13);                                // arrive + wait for the other splits
+        phase_mark(11);                                // send
+        // 2) all partial rows have landed (release / acquire at cluster scope)
+        cluster_arrive();
+        cluster_wait();
+        phase_mark(13);
         const int r0 = 128 * split / p.splits, r1 = 128 * (split + 1) / p.splits;
-        // B1: this CTA's row slice of every split is one contiguous block: stage all of them in the (idle) operand
-        //     ring with bulk copies -- one L2 round trip for the lot; 16-byte loads by the threads took ~2500 clocks
-        //     per dependent round -- then sum them in split order (deterministic) into `red`
+        // B1: sum this CTA's row slice over the splits in split order (deterministic) into `red`
         const int nrows = r1 - r0;
         const int slice_f4 = nrows * bn4;
         const uint32_t slice_bytes = (uint32_t)slice_f4 * 16u;
-        const size_t sstride4 = (size_t)128 * bn4;
-        const float4* wsl = reinterpret_cast<const float4*>(p.ws) + ((size_t)tile * p.splits * 128 + r0) * bn4;
         const float4* stage4 = reinterpret_cast<const float4*>(smem);
         float* red = reinterpret_cast<float*>(smem + (size_t)p.splits * slice_bytes);
-        if (etid == 0) {
-          asm volatile("fence.proxy.async;" ::: "memory");       // other CTAs' generic-proxy stores -> async-proxy reads
-          mbar_expect_tx(&a_full[0], slice_bytes * (uint32_t)p.splits);
-          for (int u = 0; u < p.splits; u++)
-            bulk_copy_g2s(smem + (size_t)u * slice_bytes, wsl + (size_t)u * sstride4, slice_bytes, &a_full[0]);
-        }
-        mbar_wait(&a_full[0], 0);
-        for (int e = etid; e < slice_f4; e += 256) {
-          const int c4 = e / nrows, rr = e - c4 * nrows;          // slice order is [column quad][row]
-          {
-            const int rw = r0 + rr, yy = t.y0 + rw / p.TW, xx = t.x0 + rw % p.TW;
-            if (rw >= p.TH * p.TW || yy >= p.H || xx >= p.W) continue;   // padding row: nothing parked, nothing stored
+        // `red` rows are padded by one float4: threads that walk ROWS then hit 8 different bank groups (the unpadded row
+        // stride of BN floats put a whole warp on four banks: the reduce and the epilogue below cost 5..15 k clocks)
+        const int red_ld = p.BN + 4;
+        {
+          // thread = (row rr, column quads c4, c4 + cstep, ...): one division per thread, stage reads of a warp contiguous
+          const int rr = etid % nrows, cstep = 256 / nrows;
+          const int rw = r0 + rr, yy = t.y0 + rw / p.TW, xx = t.x0 + rw % p.TW;
+          const bool rvalid = !(rw >= p.TH * p.TW || yy >= p.H || xx >= p.W);     // padding row: nothing sent, nothing stored
+          for (int c4 = etid / nrows; c4 < bn4 && cstep > 0; c4 += cstep) {
+            if (!rvalid || etid >= cstep * nrows) break;
+            float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int u = 0; u < p.splits; u++) {
+              const float4 f = stage4[(size_t)u * slice_f4 + c4 * nrows + rr];
+              acc4.x += f.x; acc4.y += f.y; acc4.z += f.z; acc4.w += f.w;
+            }
+            *reinterpret_cast<float4*>(red + (size_t)rr * red_ld + 4 * c4) = acc4;
           }
-          float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int u = 0; u < p.splits; u++) {
-            const float4 f = stage4[(size_t)u * slice_f4 + e];
-            acc4.x += f.x; acc4.y += f.y; acc4.z += f.z; acc4.w += f.w;
-          }
-          reinterpret_cast<float4*>(red)[rr * bn4 + c4] = acc4;
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         phase_mark(14);                                // B1: reduce over splits
-        // B2: (row, 32-column chunk) tasks run the real epilogue from shared memory
+        // B2: (row, 32-column chunk) tasks run the real epilogue from shared memory; consecutive threads take consecutive rows
         const int nch = out_cols_tile >> 5;
-        const int tasks = (r1 - r0) * nch;
+        const int tasks = nrows * nch;
         for (int task = etid; task < tasks; task += 256) {
-          const int rl = task / nch, c = (task % nch) << 5;
+          const int ch_i = task / nrows, rl = task - ch_i * nrows, c = ch_i << 5;
           const int rr = r0 + rl;
           const int yy = t.y0 + rr / p.TW, xx = t.x0 + rr % p.TW;
           const bool vld = (rr < p.TH * p.TW) && (yy < p.H) && (xx < p.W);
           float a[32], b[32];
-          const float4* ra = reinterpret_cast<const float4*>(red + (size_t)rl * p.BN + c);
+          const float4* ra = reinterpret_cast<const float4*>(red + (size_t)rl * red_ld + c);
 #pragma unroll
           for (int i = 0; i < 8; i++) {
             const float4 f = ra[i];
             a[4 * i] = f.x; a[4 * i + 1] = f.y; a[4 * i + 2] = f.z; a[4 * i + 3] = f.w;
           }
           if (pair) {
-            const float4* rb = reinterpret_cast<const float4*>(red + (size_t)rl * p.BN + half + c);
+            const float4* rb = reinterpret_cast<const float4*>(red + (size_t)rl * red_ld + half + c);
 #pragma unroll
             for (int i = 0; i < 8; i++) {
               const float4 f = rb[i];
@@ -907,7 +910,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             epi_finish32<false>(p, a, a, &bias_s[acc][c], &bias_s[acc][c], vld, t.img, yy, xx, pix2, o0 + c);
           if (p.gn_acc != nullptr) {
             // fused GroupNorm statistics: park the finished values (zeros for padding rows) where the accumulators were
-            float4* wr = reinterpret_cast<float4*>(red + (size_t)rl * p.BN + c);
+            float4* wr = reinterpret_cast<float4*>(red + (size_t)rl * red_ld + c);
 #pragma unroll
             for (int i = 0; i < 8; i++)
               wr[i] = vld ? make_float4(a[4 * i], a[4 * i + 1], a[4 * i + 2], a[4 * i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -918,9 +921,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           asm volatile("bar.sync 1, 256;" ::: "memory");
           const int cpg = p.cout / p.gn_groups;
           for (int col = etid; col < out_cols_tile; col += 256) {
-            float s1 = 0.f, s2 = 0.f;                   // <= 32 rows: fp32 is plenty, the cross-CTA sum is fp64
-            for (int rr = 0; rr < r1 - r0; rr++) {
-              const float xv = red[(size_t)rr * p.BN + col];
+            float s1 = 0.f, s2 = 0.f;                   // <= 43 rows: fp32 is plenty, the cross-CTA sum is fp64
+            for (int rr = 0; rr < nrows; rr++) {
+              const float xv = red[(size_t)rr * red_ld + col];
               s1 += xv;
               s2 += xv * xv;
             }
@@ -929,16 +932,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             atomicAdd(dst + 1, (double)s2);
           }
         }
-        // last CTA to finish re-arms the counters (nobody can still be spinning: all have passed the wait)
-        asm volatile("bar.sync 1, 256;" ::: "memory");
         phase_mark(15);                                // B2: epilogue + statistics
-        if (etid == 0) {
-          const int old = atomicAdd(p.counters + p.counters_half + tile, 1);
-          if (old == p.splits - 1) {
-            p.counters[tile] = 0;
-            p.counters[p.counters_half + tile] = 0;
-          }
-        }
         continue;
       }
       if (fast) {

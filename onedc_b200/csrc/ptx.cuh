@@ -76,6 +76,24 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
+// ---------------------------------------------------------------- thread-block clusters / distributed shared memory
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the location `saddr` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // Polling wait with a sleep between polls.  A warp that spins on mbarrier.try_wait floods the MIO queue of its scheduler
 // with SYNCS instructions; a softmax warp on the same scheduler then waits for that queue with every MUFU / tcgen05.ld it
 // issues (attention.cu: the two softmax warps that share schedulers with the TMA and MMA warps ran ~50 % slower).
