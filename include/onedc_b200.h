@@ -103,8 +103,9 @@ typedef struct {
   int32_t bn;           /* N tile, multiple of 16 (32 for pair modes), <= 256; 0 = auto */
   int32_t impl;         /* 0 = tcgen05 kernel, 1 = SIMT checking kernel (debug only), 2 = dry run: validate and
                            decide (tiling, split-K, fused statistics) without launching (bench bookkeeping) */
-  /* optional split-K scratch (layers with too few tiles to fill the GPU): fp32 workspace and per-tile int32
-   * arrival counters that are zero on entry and zero again on exit; NULL disables split-K */
+  /* split-K switch (layers with too few tiles to fill the GPU): non-NULL splitk_ws / splitk_counters allow it, NULL
+   * disables it.  Since round 2 the splits of a tile run as one thread-block cluster and reduce over distributed
+   * shared memory: the buffers are not touched any more (kept in the ABI; splitk_ws_floats still bounds tiles x splits) */
   void* splitk_ws;
   int64_t splitk_ws_floats;
   void* splitk_counters;

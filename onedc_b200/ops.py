@@ -203,8 +203,9 @@ SPLITK = os.environ.get("ONEDC_SPLITK", "1") == "1"
 
 
 def _splitk_buffers(device):
-    """fp32 partial-tile workspace (148 tiles x 128 x 256) + self-cleaning arrival counters, shared by all launches
-    of a stream (launches are stream-ordered, so one scratch is enough)."""
+    """Split-K switch of onedc_igemm: non-NULL buffers allow it.  (Round 1 parked fp32 partial tiles here behind arrival
+    counters; the cluster / distributed-shared-memory reduction of round 2 no longer touches them, only their size is
+    still read as a bound on tiles x splits.)"""
     key = (str(device), SCRATCH_LANE)
     if key not in _splitk_scratch:
         _splitk_scratch[key] = (torch.empty(160 * 128 * 256, device=device, dtype=torch.float32),
