@@ -1206,6 +1206,15 @@ static void pick_tile(int H, int W, int* th, int* tw) {
 
 static long long* g_igemm_dbg = nullptr;
 
+// Shortest K loop (in 64-channel x tap iterations) that is split.  A cluster launch plus the exchange costs ~8 us; measured
+// on B200 (round 2, L2-flushed single launches, split vs plain): 48x48 512->512 3x3 (72 iterations) 24.6 vs 18.4 us and
+// 576 x 5120->1280 (80) 22.5 vs 20.5 us -- plain wins; 24x24 1280->1280 3x3 (180) 32.8 vs 34.8, 12x12 1280->1280 3x3 (180)
+// 20.5 vs 34.8, 24x24 2560->1280 3x3 (360) 52.2 vs 59.4 -- split wins.
+static int split_min_kiters() {
+  static const char* e = getenv("ONEDC_SPLITK_MIN_KITERS");
+  return e != nullptr ? atoi(e) : 100;
+}
+
 // clusters of `size` split-K CTAs (one CTA per SM: 200 KB of shared memory) that the device can hold at once
 static int max_active_clusters(int size) {
   static int cache[17] = {0};
@@ -1274,7 +1283,7 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
     const int mt = d->n_img * ((Ho + th0 - 1) / th0) * ((Wo + tw0 - 1) / tw0);
     const int taps0 = d->ntaps > 0 ? d->ntaps : d->ksize * d->ksize;
     const int kit = taps0 * ((d->a_c[0] + 63) / 64 + (d->a_c[1] + 63) / 64);
-    const bool will_split = !d->deterministic && d->splitk_ws != nullptr && mt * p.n_tiles * 2 <= sm_count() && kit >= 32 &&
+    const bool will_split = !d->deterministic && d->splitk_ws != nullptr && mt * p.n_tiles * 2 <= sm_count() && kit >= split_min_kiters() &&
                             sm_count() / (mt * p.n_tiles) >= 4;
     while (!will_split && p.BN % 64 == 0 && p.BN >= 128 && d->cout % (p.BN / 2) == 0 &&
            mt * ((d->cout + p.BN / 2 - 1) / (p.BN / 2)) <= sm_count()) {
@@ -1375,7 +1384,7 @@ static int igemm_launch(onedc_igemm_desc* d, cudaStream_t stream) {
     const bool fast_all = p.vec_ok && (d->cout % p.BN == 0) && (octile % 32 == 0) &&
                           (d->store_mode == ST_NORMAL || d->store_mode == ST_QUAD || (d->store_mode == ST_PIXSHUF && d->ps_c % 32 == 0));
     if (d->impl != 1 && !d->deterministic && p.ws != nullptr && p.counters != nullptr && fast_all && tiles * 2 <= sm_count() &&
-        kiters >= 16 && tiles <= d->splitk_max_tiles / 2) {
+        kiters >= split_min_kiters() && tiles <= d->splitk_max_tiles / 2) {
       int s = sm_count() / tiles;
       if (s > kiters / 8) s = kiters / 8;
       // The splits of a tile wait for each other (arrival counter), so they are launched as one thread-block cluster:
