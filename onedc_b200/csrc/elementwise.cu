@@ -295,32 +295,46 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_kernel(const __nv_bfloat16* 
         if (okr) r[2] = __ldg(rp + nvec);
       }
     };
-    uint2 win[3][3];
+    // two output rows per iteration: rows yy-1 .. yy+2 in win[0..3], six loads issued together, two independent FMA chains
+    uint2 win[4][3];
     load_row(y0 - 1, win[0]);
     load_row(y0, win[1]);
-    for (int yy = y0; yy < y1; yy++) {
+    for (int yy = y0; yy < y1; yy += 2) {
       load_row(yy + 1, win[2]);
-      float a0 = bs.x, a1 = bs.y, a2 = bs.z, a3 = bs.w;
+      load_row(yy + 2 <= y1 ? yy + 2 : h, win[3]);            // row y1 is only read as the halo of row y1 - 1
+      float a[2][4];
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        a[r][0] = bs.x; a[r][1] = bs.y; a[r][2] = bs.z; a[r][3] = bs.w;
+      }
 #pragma unroll
       for (int ky = 0; ky < 3; ky++) {
 #pragma unroll
         for (int kx = 0; kx < 3; kx++) {
-          const uint2 q = win[ky][kx];
           const float4 wv = wk[ky * 3 + kx];
-          a0 = fmaf(bf16lo(q.x), wv.x, a0);
-          a1 = fmaf(bf16hi(q.x), wv.y, a1);
-          a2 = fmaf(bf16lo(q.y), wv.z, a2);
-          a3 = fmaf(bf16hi(q.y), wv.w, a3);
+#pragma unroll
+          for (int r = 0; r < 2; r++) {
+            const uint2 q = win[ky + r][kx];
+            a[r][0] = fmaf(bf16lo(q.x), wv.x, a[r][0]);
+            a[r][1] = fmaf(bf16hi(q.x), wv.y, a[r][1]);
+            a[r][2] = fmaf(bf16lo(q.y), wv.z, a[r][2]);
+            a[r][3] = fmaf(bf16hi(q.y), wv.w, a[r][3]);
+          }
         }
       }
-      uint2 o;
-      o.x = pack_bf16x2(a0, a1);
-      o.y = pack_bf16x2(a2, a3);
-      reinterpret_cast<uint2*>(out + (((long long)n * h + yy) * w + xx) * c)[v] = o;
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        if (yy + r < y1) {
+          uint2 o;
+          o.x = pack_bf16x2(a[r][0], a[r][1]);
+          o.y = pack_bf16x2(a[r][2], a[r][3]);
+          reinterpret_cast<uint2*>(out + (((long long)n * h + yy + r) * w + xx) * c)[v] = o;
+        }
+      }
 #pragma unroll
       for (int kx = 0; kx < 3; kx++) {
-        win[0][kx] = win[1][kx];
-        win[1][kx] = win[2][kx];
+        win[0][kx] = win[2][kx];
+        win[1][kx] = win[3][kx];
       }
     }
   }
