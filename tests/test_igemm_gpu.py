@@ -174,6 +174,33 @@ def test_split_k_small_m_layers(cuda, h, w, cin, cout, two):
     _close(ops.igemm(x, cw, x2=x2, res=res, impl=1), ref)
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 12, 20, 1280, 1280), (1, 24, 24, 1920, 640), (3, 9, 7, 1280, 320)])
+def test_split_k_cluster_reduction_with_statistics(cuda, n, h, w, cin, cout):
+    """Split-K runs as thread-block clusters that reduce over distributed shared memory: several images, ragged tiles (rows
+    that no CTA sends), row slices that do not divide 128, bias + residual, and the fused GroupNorm statistics taken from the
+    reduced rows must match torch; bit-identical run to run."""
+    from onedc_b200 import ops
+    x = _mk((n, h, w, cin), cuda, 1)
+    wt = _mk((cout, cin, 3, 3), "cpu", 2, scale=(cin * 9) ** -0.5).float()
+    b = _mk((cout,), "cpu", 3).float()
+    res = _mk((n, h, w, cout), cuda, 4)
+    cw = ops.ConvW(wt, b, cuda)
+    ops.gn_arena_reset(cuda)
+    out = ops.igemm(x, cw, res=res, stats=True)
+    ref = _ref_conv(x, cw.w[:9].float().reshape(3, 3, cout, cin).permute(2, 3, 0, 1).contiguous(), b.to(cuda), 3, 1) + res.float()
+    _close(out, ref)
+    acc = getattr(out, "_gn_acc", None)
+    if acc is not None:
+        torch.cuda.synchronize()
+        ng = cout if out._gn_chan else 32
+        got = acc[: n * ng * 2].view(n, ng, 2)
+        o = out.float().view(n, h * w, ng, cout // ng)
+        want = torch.stack([o.sum(dim=(1, 3)), (o * o).sum(dim=(1, 3))], dim=-1).double()
+        assert torch.allclose(got, want, rtol=3e-3, atol=1e-3 * float(want.abs().max()))
+    ops.gn_arena_reset(cuda)
+    assert torch.equal(out, ops.igemm(x, cw, res=res, stats=True)), "not deterministic"
+
+
 @pytest.mark.parametrize("n,h,w,c,co", [(1, 24, 24, 256, 256), (2, 12, 20, 512, 512), (1, 48, 48, 1280, 1280)])
 def test_folded_upsample_conv(cuda, n, h, w, c, co):
     """nearest-2x + conv3x3 folded into four 4-tap convs on the low-res input == the unfolded computation."""
