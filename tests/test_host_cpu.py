@@ -330,3 +330,32 @@ def test_sharding_world2_gloo(tmp_path):
     assert sorted(res[0]["mine"] + res[1]["mine"]) == list(range(13))
     assert not set(res[0]["mine"]) & set(res[1]["mine"])
     assert all(r["tmax"] == 2.0 and r["total"] == 13 for r in res)
+
+
+def test_bench_cpu_baseline_is_bounded(monkeypatch):
+    """bench.py runs the CPU baseline in a child process under a time limit and keeps the last complete record; the thread
+    count follows the affinity mask / cgroup quota, never the machine's core count."""
+    import subprocess
+    sys.path.insert(0, ROOT)
+    import bench
+    n = bench._host_cores()
+    assert 1 <= n <= 64 and n <= (os.cpu_count() or 1)
+
+    class FakeProc:
+        def __init__(self, *a, **k):
+            self.calls = 0
+
+        def communicate(self, timeout=None):
+            self.calls += 1
+            if self.calls == 1:
+                raise subprocess.TimeoutExpired("child", timeout)
+            return ('{"value": 0.1, "unit": "MP/s", "cores": 4, "kind": "port", "sample": "1 x"}\n{"value": 0.2, "unit": "MP/s", '
+                    '"cores": 4, "kind": "port", "sample": "2 x"}\n{"value": 0.3, "unit"', "")
+
+        def kill(self):
+            pass
+
+    monkeypatch.setattr(subprocess, "Popen", FakeProc)
+    rec = bench.cpu_baseline_bounded(type("A", (), {"size": 768})(), limit_s=0.01)
+    assert rec["value"] == 0.2 and rec["kind"] == "port" and "truncated" in rec     # the torn last line is ignored
+
