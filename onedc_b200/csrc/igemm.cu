@@ -267,13 +267,25 @@ __device__ __forceinline__ void chunk_group_stats(const float* a, bool valid, in
   *q_out = warp_group_sum<NG>(gq, lane);
 }
 
+// Epilogue switches of a launch packed into one register (epi_flags): tested per 32-column chunk.  Read from the parameter
+// block instead, every test was a dependent LDCU -> UISETP -> BRA.U chain of ~70 clocks, seven per chunk: a third of the
+// 9000 clocks that the epilogue of a 128 x 256 tile took (the small-K layers are bound by exactly that).
+enum : uint32_t { EF_LRELU = 1, EF_SILU = 2, EF_GELU = 4, EF_RES = 8, EF_RES_BF16 = 16, EF_PIXSHUF = 32, EF_QUAD = 64, EF_OUT_BF16 = 128,
+                  EF_PAIR_LRELU = 256 };
+__device__ __forceinline__ uint32_t epi_flags(const IgemmParams& p) {
+  return (p.act == ACT_LRELU ? EF_LRELU : 0u) | (p.act == ACT_SILU ? EF_SILU : 0u) | (p.act == ACT_GELU ? EF_GELU : 0u) |
+         (p.res != nullptr ? EF_RES : 0u) | (p.res_dtype == DT_BF16 ? EF_RES_BF16 : 0u) |
+         (p.store_mode == ST_PIXSHUF ? EF_PIXSHUF : 0u) | (p.store_mode == ST_QUAD ? EF_QUAD : 0u) |
+         (p.out_dtype == DT_BF16 ? EF_OUT_BF16 : 0u) | (p.epi_mode == EPI_PAIR_LRELU ? EF_PAIR_LRELU : 0u);
+}
+
 // Finishes 32 output columns of one pixel: v[] already holds accumulator (+ nothing else) values.
 //   a[32]: accumulators of GEMM columns (n0 + c ..), b[32]: partner columns (pair modes only)
 //   bias_a / bias_b: shared-memory bias slices aligned with a / b
 template <bool PAIR>
 __device__ __forceinline__ void epi_finish32(const IgemmParams& p, float* a, const float* b, const float* bias_a,
                                              const float* bias_b, bool valid, int img, int y, int x, long long pix,
-                                             int ocol) {
+                                             int ocol, const uint32_t fl) {
   float* v = a;
   if (!PAIR) {
     const float4* ba = reinterpret_cast<const float4*>(bias_a);
@@ -282,13 +294,13 @@ __device__ __forceinline__ void epi_finish32(const IgemmParams& p, float* a, con
       const float4 a4 = ba[i];
       v[4 * i + 0] += a4.x; v[4 * i + 1] += a4.y; v[4 * i + 2] += a4.z; v[4 * i + 3] += a4.w;
     }
-    if (p.act == ACT_LRELU) {
+    if (fl & EF_LRELU) {
 #pragma unroll
       for (int i = 0; i < 32; i++) v[i] = v[i] > 0.f ? v[i] : v[i] * p.slope;
-    } else if (p.act == ACT_SILU) {
+    } else if (fl & EF_SILU) {
 #pragma unroll
       for (int i = 0; i < 32; i++) v[i] = __fdividef(v[i], 1.f + __expf(-v[i]));
-    } else if (p.act == ACT_GELU) {
+    } else if (fl & EF_GELU) {
 #pragma unroll
       for (int i = 0; i < 32; i++) v[i] = gelu_erf(v[i]);
     }
@@ -303,7 +315,7 @@ __device__ __forceinline__ void epi_finish32(const IgemmParams& p, float* a, con
       for (int j = 0; j < 4; j++) {
         const float va = a[4 * i + j] + av[j];
         const float vb = b[4 * i + j] + bv[j];
-        if (p.epi_mode == EPI_PAIR_LRELU)
+        if (fl & EF_PAIR_LRELU)
           v[4 * i + j] = (va > 0.f ? va : 0.1f * va) + (vb > 0.f ? vb : 0.01f * vb);
         else
           v[4 * i + j] = va * gelu_erf(vb);
@@ -311,8 +323,8 @@ __device__ __forceinline__ void epi_finish32(const IgemmParams& p, float* a, con
     }
   }
   if (!valid) return;
-  if (p.res != nullptr) {
-    if (p.res_dtype == DT_BF16) {
+  if (fl & EF_RES) {
+    if (fl & EF_RES_BF16) {
       const uint4* r4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.res_ld + ocol);
       uint4 qv[4];
 #pragma unroll
@@ -335,15 +347,15 @@ __device__ __forceinline__ void epi_finish32(const IgemmParams& p, float* a, con
   }
   long long opix = pix;
   int oc = ocol;
-  if (p.store_mode == ST_PIXSHUF) {
+  if (fl & EF_PIXSHUF) {
     const int qd = ocol / p.ps_c;
     oc = ocol - qd * p.ps_c;
     opix = ((long long)img * (2 * p.H) + (2 * y + (qd >> 1))) * (2 * p.W) + (2 * x + (qd & 1));
-  } else if (p.store_mode == ST_QUAD) {
+  } else if (fl & EF_QUAD) {
     opix = ((long long)img * (2 * p.H) + (2 * y + (p.quad >> 1))) * (2 * p.W) + (2 * x + (p.quad & 1));
   }
   const long long o = opix * p.out_ld + p.out_col_off + oc;
-  if (p.out_dtype == DT_BF16) {
+  if (fl & EF_OUT_BF16) {
     uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -707,6 +719,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     const int half = p.BN >> 1;
     const int out_cols_tile = pair ? half : p.BN;      // output columns produced per tile
     float csum[4] = {0.f, 0.f, 0.f, 0.f}, csq[4] = {0.f, 0.f, 0.f, 0.f};   // fused GroupNorm statistics
+    const uint32_t eflags = epi_flags(p);
     const long long t_epi0 = TIMED ? clock64() : 0;
     int st_img = -1, st_nt = -1;
     int it = 0;
@@ -905,9 +918,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
           }
           const long long pix2 = ((long long)t.img * p.H + yy) * p.W + xx;
           if (pair)
-            epi_finish32<true>(p, a, b, &bias_s[acc][c], &bias_s[acc][half + c], vld, t.img, yy, xx, pix2, o0 + c);
+            epi_finish32<true>(p, a, b, &bias_s[acc][c], &bias_s[acc][half + c], vld, t.img, yy, xx, pix2, o0 + c, eflags);
           else
-            epi_finish32<false>(p, a, a, &bias_s[acc][c], &bias_s[acc][c], vld, t.img, yy, xx, pix2, o0 + c);
+            epi_finish32<false>(p, a, a, &bias_s[acc][c], &bias_s[acc][c], vld, t.img, yy, xx, pix2, o0 + c, eflags);
           if (p.gn_acc != nullptr) {
             // fused GroupNorm statistics: park the finished values (zeros for padding rows) where the accumulators were
             float4* wr = reinterpret_cast<float4*>(red + (size_t)rl * red_ld + c);
@@ -976,9 +989,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             for (int i = 0; i < 32; i++) a[i] = __uint_as_float(r[i]);
           }
           if (pair)
-            epi_finish32<true>(p, a, b, &bias_s[acc][c], &bias_s[acc][half + c], valid, t.img, y, x, pix, o0 + c);
+            epi_finish32<true>(p, a, b, &bias_s[acc][c], &bias_s[acc][half + c], valid, t.img, y, x, pix, o0 + c, eflags);
           else
-            epi_finish32<false>(p, a, a, &bias_s[acc][c], &bias_s[acc][c], valid, t.img, y, x, pix, o0 + c);
+            epi_finish32<false>(p, a, a, &bias_s[acc][c], &bias_s[acc][c], valid, t.img, y, x, pix, o0 + c, eflags);
           if (want_stats) {
             // GroupNorm statistics of what was just stored: per-group sums over this warp's 32 rows, kept in
             // registers across the CTA's tiles, flushed with one fp64 atomic per group when the tile column changes
