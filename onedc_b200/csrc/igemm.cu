@@ -285,7 +285,7 @@ __device__ __forceinline__ uint32_t epi_flags(const IgemmParams& p) {
 template <bool PAIR>
 __device__ __forceinline__ void epi_finish32(const IgemmParams& p, float* a, const float* b, const float* bias_a,
                                              const float* bias_b, bool valid, int img, int y, int x, long long pix,
-                                             int ocol, const uint32_t fl) {
+                                             int ocol, const uint32_t fl, uint4* stg = nullptr, int lane = 0) {
   float* v = a;
   if (!PAIR) {
     const float4* ba = reinterpret_cast<const float4*>(bias_a);
@@ -322,8 +322,10 @@ __device__ __forceinline__ void epi_finish32(const IgemmParams& p, float* a, con
       }
     }
   }
-  if (!valid) return;
-  if (fl & EF_RES) {
+  if (!valid && stg == nullptr) return;
+  // (fetching the residual rows the same way -- four lanes per row through the tile -- measured slower: the loads' latency
+  // then sits in front of two more synchronisations; kept row per lane)
+  if (valid && (fl & EF_RES)) {
     if (fl & EF_RES_BF16) {
       const uint4* r4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.res) + pix * p.res_ld + ocol);
       uint4 qv[4];
@@ -356,17 +358,37 @@ __device__ __forceinline__ void epi_finish32(const IgemmParams& p, float* a, con
   }
   const long long o = opix * p.out_ld + p.out_col_off + oc;
   if (fl & EF_OUT_BF16) {
-    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
+    uint4 w4[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      uint4 w4;
-      w4.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-      w4.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-      w4.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-      w4.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-      dst[i] = w4;
+      w4[i].x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+      w4[i].y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+      w4[i].z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+      w4[i].w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
     }
-  } else {
+    if (stg != nullptr) {
+      // Row-per-lane stores touch 32 different 128-byte lines per instruction (16 bytes each) and the store path, not the
+      // tensor pipe, bounded every layer with a short K loop (9000 clocks of epilogue per 128 x 256 tile).  The warp's
+      // 32 rows x 64 bytes go through a warp-private shared-memory tile (row pitch 80 bytes: conflict-free) so that
+      // four lanes write one row's 64 contiguous bytes: 8 lines per instruction instead of 32.
+#pragma unroll
+      for (int i = 0; i < 4; i++) stg[lane * 5 + i] = w4[i];
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int r = 8 * i + (lane >> 2);
+        const uint4 wv = stg[r * 5 + (lane & 3)];
+        const long long orow = __shfl_sync(0xffffffffu, o, r);
+        const int vrow = __shfl_sync(0xffffffffu, valid ? 1 : 0, r);
+        if (vrow) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + orow + (lane & 3) * 8) = wv;
+      }
+      __syncwarp();
+    } else {
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
+#pragma unroll
+      for (int i = 0; i < 4; i++) dst[i] = w4[i];
+    }
+  } else if (valid) {
     float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
 #pragma unroll
     for (int i = 0; i < 8; i++) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -428,6 +450,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
   __shared__ __align__(8) uint64_t tmem_empty[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float bias_s[2][256];
+  __shared__ __align__(16) uint4 store_stage[kEpiWarps][32 * 5];   // epilogue warps' private 32 x 64-byte transpose tiles (pitch 80 B)
 
   // broadcast from lane 0 so that the compiler KNOWS the warp index is warp-uniform (role branches stay uniform)
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -720,6 +743,7 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     const int out_cols_tile = pair ? half : p.BN;      // output columns produced per tile
     float csum[4] = {0.f, 0.f, 0.f, 0.f}, csq[4] = {0.f, 0.f, 0.f, 0.f};   // fused GroupNorm statistics
     const uint32_t eflags = epi_flags(p);
+    uint4* stg_w = (eflags & EF_OUT_BF16) ? store_stage[warp - 2] : nullptr;
     const long long t_epi0 = TIMED ? clock64() : 0;
     int st_img = -1, st_nt = -1;
     int it = 0;
@@ -989,9 +1013,9 @@ igemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             for (int i = 0; i < 32; i++) a[i] = __uint_as_float(r[i]);
           }
           if (pair)
-            epi_finish32<true>(p, a, b, &bias_s[acc][c], &bias_s[acc][half + c], valid, t.img, y, x, pix, o0 + c, eflags);
+            epi_finish32<true>(p, a, b, &bias_s[acc][c], &bias_s[acc][half + c], valid, t.img, y, x, pix, o0 + c, eflags, stg_w, lane);
           else
-            epi_finish32<false>(p, a, a, &bias_s[acc][c], &bias_s[acc][c], valid, t.img, y, x, pix, o0 + c, eflags);
+            epi_finish32<false>(p, a, a, &bias_s[acc][c], &bias_s[acc][c], valid, t.img, y, x, pix, o0 + c, eflags, stg_w, lane);
           if (want_stats) {
             // GroupNorm statistics of what was just stored: per-group sums over this warp's 32 rows, kept in
             // registers across the CTA's tiles, flushed with one fp64 atomic per group when the tile column changes
